@@ -1,0 +1,274 @@
+// Velocity-Verlet halves, the thermo kinetic-energy reduction, PBC wrap, and the halo
+// (ghost atom) kernels.  Replaces Integrate::initialIntegrate/finalIntegrate
+// (ref/integrate.cpp:46-68), Thermo::temperature's loop (ref/thermo.cpp:149-157), Atom::pbc
+// (ref/atom.cpp:106-122) and Atom::pack_comm/unpack_comm/pack_reverse/unpack_reverse/
+// pack_border/unpack_border (ref/atom.cpp:135-226) as used by Comm (ref/comm.cpp:276-883).
+#pragma once
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace mmd {
+
+// ---- integrate --------------------------------------------------------------------------
+// One atom per thread, one aligned vector access per array.  ZERO_F additionally clears f
+// after it has been consumed (the force prologue of the half-list kernels, fused here so the
+// step needs no separate memset over the local atoms).
+template <class T, int ZERO_F>
+__global__ void initial_integrate_kernel(Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ v, Vec4<T>* __restrict__ f,
+                                         int nlocal, T dt, T dtforce) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  Vec4<T> xi = x[i], vi = v[i];
+  const Vec4<T> fi = f[i];
+  vi.x += dtforce * fi.x;
+  vi.y += dtforce * fi.y;
+  vi.z += dtforce * fi.z;
+  xi.x += dt * vi.x;
+  xi.y += dt * vi.y;
+  xi.z += dt * vi.z;
+  x[i] = xi;
+  v[i] = vi;
+  if (ZERO_F) {
+    Vec4<T> z; z.x = z.y = z.z = z.w = (T)0;
+    f[i] = z;
+  }
+}
+
+// KE: also accumulate sum_i (v.v)*mass of the UPDATED velocities into *ke (fused thermo).
+template <class T, int KE>
+__global__ void final_integrate_kernel(Vec4<T>* __restrict__ v, const Vec4<T>* __restrict__ f, int nlocal, T dtforce,
+                                       T mass, double* __restrict__ ke) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double e = 0.0;
+  if (i < nlocal) {
+    Vec4<T> vi = v[i];
+    const Vec4<T> fi = f[i];
+    vi.x += dtforce * fi.x;
+    vi.y += dtforce * fi.y;
+    vi.z += dtforce * fi.z;
+    v[i] = vi;
+    if (KE) e = (double)((vi.x * vi.x + vi.y * vi.y + vi.z * vi.z) * mass);
+  }
+  if (KE) {
+    const double a[1] = {e};
+    block_accumulate<1>(a, ke);
+  }
+}
+
+template <class T>
+__global__ void sum_mv2_kernel(const Vec4<T>* __restrict__ v, int nlocal, T mass, double* __restrict__ out) {
+  double e = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nlocal; i += gridDim.x * blockDim.x) {
+    const Vec4<T> vi = v[i];
+    e += (double)((vi.x * vi.x + vi.y * vi.y + vi.z * vi.z) * mass);
+  }
+  const double a[1] = {e};
+  block_accumulate<1>(a, out);
+}
+
+// ---- PBC ----------------------------------------------------------------------------------
+// Two sequential tests per axis, in the reference's order (ref/atom.cpp:106-122).
+template <class T> __global__ void pbc_kernel(Vec4<T>* __restrict__ x, int nlocal, T xprd, T yprd, T zprd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  Vec4<T> p = x[i];
+  if (p.x < (T)0) p.x += xprd;
+  if (p.x >= xprd) p.x -= xprd;
+  if (p.y < (T)0) p.y += yprd;
+  if (p.y >= yprd) p.y -= yprd;
+  if (p.z < (T)0) p.z += zprd;
+  if (p.z >= zprd) p.z -= zprd;
+  x[i] = p;
+}
+
+// ---- halo: per-step forward / reverse ------------------------------------------------------
+// A "swap pair" is the two swaps of one dimension layer (send down / send up); they read the
+// same source range and write disjoint ghost ranges, so one launch covers both.
+struct SwapPairDev {
+  const int* list[2];  // Comm::sendlist
+  int count[2];        // Comm::sendnum (self swap: == recvnum)
+  int first[2];        // Comm::firstrecv
+  int any[2];          // Comm::pbc_any
+  int flag[2][3];      // Comm::pbc_flagx/y/z
+};
+
+// self-swap forward: x[first+k] = x[list[k]] + flag*prd, type carried along in the 4th lane
+// (pack_comm + unpack_comm fused, no staging buffer).  ZERO_F also clears the ghost's force
+// (half-list prologue, ref/force_lj.cpp:195-199).
+template <class T, int ZERO_F>
+__global__ void halo_forward_self_kernel(Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, SwapPairDev sp, T xprd,
+                                         T yprd, T zprd) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  int s = 0;
+  if (k >= sp.count[0]) { k -= sp.count[0]; s = 1; }
+  if (k >= sp.count[s]) return;
+  Vec4<T> p = x[sp.list[s][k]];
+  if (sp.any[s]) {
+    p.x = p.x + sp.flag[s][0] * xprd;
+    p.y = p.y + sp.flag[s][1] * yprd;
+    p.z = p.z + sp.flag[s][2] * zprd;
+  }
+  x[sp.first[s] + k] = p;
+  if (ZERO_F) {
+    Vec4<T> z; z.x = z.y = z.z = z.w = (T)0;
+    f[sp.first[s] + k] = z;
+  }
+}
+
+// self-swap reverse: f[list[k]] += f[first+k]  (pack_reverse + unpack_reverse fused).
+// REDG because the two swaps of a pair (and, in tiny boxes, one list) may name an atom twice.
+template <class T>
+__global__ void halo_reverse_self_kernel(Vec4<T>* __restrict__ f, SwapPairDev sp) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  int s = 0;
+  if (k >= sp.count[0]) { k -= sp.count[0]; s = 1; }
+  if (k >= sp.count[s]) return;
+  const Vec4<T> g = f[sp.first[s] + k];
+  red_add3(f + sp.list[s][k], g.x, g.y, g.z);
+}
+
+// remote swaps: pack to / unpack from a contiguous buffer that NCCL moves (3 reals per atom,
+// the reference's wire format, ref/atom.cpp:135-195)
+template <class T>
+__global__ void halo_pack_x_kernel(const Vec4<T>* __restrict__ x, const int* __restrict__ list, int n, int any, int fx,
+                                   int fy, int fz, T xprd, T yprd, T zprd, T* __restrict__ buf) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  Vec4<T> p = x[list[k]];
+  if (any) {
+    p.x = p.x + fx * xprd;
+    p.y = p.y + fy * yprd;
+    p.z = p.z + fz * zprd;
+  }
+  buf[3 * k + 0] = p.x;
+  buf[3 * k + 1] = p.y;
+  buf[3 * k + 2] = p.z;
+}
+template <class T, int ZERO_F>
+__global__ void halo_unpack_x_kernel(Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, int first, int n,
+                                     const T* __restrict__ buf) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  Vec4<T> p = x[first + k];  // keeps the type lane set by borders
+  p.x = buf[3 * k + 0];
+  p.y = buf[3 * k + 1];
+  p.z = buf[3 * k + 2];
+  x[first + k] = p;
+  if (ZERO_F) {
+    Vec4<T> z; z.x = z.y = z.z = z.w = (T)0;
+    f[first + k] = z;
+  }
+}
+template <class T>
+__global__ void halo_pack_f_kernel(const Vec4<T>* __restrict__ f, int first, int n, T* __restrict__ buf) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const Vec4<T> g = f[first + k];
+  buf[3 * k + 0] = g.x;
+  buf[3 * k + 1] = g.y;
+  buf[3 * k + 2] = g.z;
+}
+template <class T>
+__global__ void halo_unpack_f_kernel(Vec4<T>* __restrict__ f, const int* __restrict__ list, int n,
+                                     const T* __restrict__ buf) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  red_add3(f + list[k], buf[3 * k + 0], buf[3 * k + 1], buf[3 * k + 2]);
+}
+
+// scalar per-atom forward halo (EAM fp, ForceEAM::communicate ref/force_eam.cpp:851-914)
+template <class T>
+__global__ void halo_forward_scalar_self_kernel(T* __restrict__ a, SwapPairDev sp) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  int s = 0;
+  if (k >= sp.count[0]) { k -= sp.count[0]; s = 1; }
+  if (k >= sp.count[s]) return;
+  a[sp.first[s] + k] = a[sp.list[s][k]];
+}
+template <class T>
+__global__ void gather_scalar_kernel(const T* __restrict__ a, const int* __restrict__ list, int n, T* __restrict__ buf) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) buf[k] = a[list[k]];
+}
+
+// ---- borders: ordered slab selection --------------------------------------------------------
+// Atoms i in [nfirst,nlast) with lo <= x[dim] <= hi (both inclusive, ref/comm.cpp:776) are
+// appended to the send list IN INDEX ORDER (the reference's order), for both swaps of a pair at
+// once.  Three phases share the generic scan spine: per-tile counts, spine, ordered scatter.
+constexpr int BORDER_THREADS = 256;
+
+template <class T>
+__device__ __forceinline__ T coord_of(const Vec4<T>& p, int dim) { return dim == 0 ? p.x : (dim == 1 ? p.y : p.z); }
+
+template <class T>
+__global__ void border_count_kernel(const Vec4<T>* __restrict__ x, int nfirst, int nlast, int dim, T lo0, T hi0, T lo1,
+                                    T hi1, int* __restrict__ tile_counts0, int* __restrict__ tile_counts1) {
+  const int i = nfirst + blockIdx.x * BORDER_THREADS + threadIdx.x;
+  int m0 = 0, m1 = 0;
+  if (i < nlast) {
+    const T c = coord_of(x[i], dim);
+    m0 = (c >= lo0 && c <= hi0);
+    m1 = (c >= lo1 && c <= hi1);
+  }
+  int t0, t1;
+  block_exclusive_scan(m0, &t0);
+  block_exclusive_scan(m1, &t1);
+  if (threadIdx.x == 0) {
+    tile_counts0[blockIdx.x] = t0;
+    tile_counts1[blockIdx.x] = t1;
+  }
+}
+
+// writes list entries; for self swaps also materialises the ghost (pack_border+unpack_border).
+// first1 (start of the second swap's ghosts) = first0 + total0 is passed by the host after it
+// has read the totals (it needs them anyway to grow the arrays).
+template <class T>
+__global__ void border_scatter_kernel(Vec4<T>* __restrict__ x, int nfirst, int nlast, int dim, T lo0, T hi0, T lo1,
+                                      T hi1, const int* __restrict__ tile_off0, const int* __restrict__ tile_off1,
+                                      int* __restrict__ list0, int* __restrict__ list1, int self0, int self1, int first0,
+                                      int first1, SwapPairDev sp, T xprd, T yprd, T zprd, T* __restrict__ buf0,
+                                      T* __restrict__ buf1) {
+  const int i = nfirst + blockIdx.x * BORDER_THREADS + threadIdx.x;
+  int m0 = 0, m1 = 0;
+  Vec4<T> p;
+  p.x = p.y = p.z = p.w = (T)0;
+  if (i < nlast) {
+    p = x[i];
+    const T c = coord_of(p, dim);
+    m0 = (c >= lo0 && c <= hi0);
+    m1 = (c >= lo1 && c <= hi1);
+  }
+  int t0, t1;
+  const int e0 = block_exclusive_scan(m0, &t0) + tile_off0[blockIdx.x];
+  const int e1 = block_exclusive_scan(m1, &t1) + tile_off1[blockIdx.x];
+  const T prd[3] = {xprd, yprd, zprd};
+  if (m0) {
+    list0[e0] = i;
+    Vec4<T> q = p;
+    if (sp.any[0]) { q.x = q.x + sp.flag[0][0] * prd[0]; q.y = q.y + sp.flag[0][1] * prd[1]; q.z = q.z + sp.flag[0][2] * prd[2]; }
+    if (self0) x[first0 + e0] = q;
+    else { buf0[4 * e0 + 0] = q.x; buf0[4 * e0 + 1] = q.y; buf0[4 * e0 + 2] = q.z; buf0[4 * e0 + 3] = (T)lane_to_type(q.w); }
+  }
+  if (m1) {
+    list1[e1] = i;
+    Vec4<T> q = p;
+    if (sp.any[1]) { q.x = q.x + sp.flag[1][0] * prd[0]; q.y = q.y + sp.flag[1][1] * prd[1]; q.z = q.z + sp.flag[1][2] * prd[2]; }
+    if (self1) x[first1 + e1] = q;
+    else { buf1[4 * e1 + 0] = q.x; buf1[4 * e1 + 1] = q.y; buf1[4 * e1 + 2] = q.z; buf1[4 * e1 + 3] = (T)lane_to_type(q.w); }
+  }
+}
+
+// unpack_border for remote swaps: 4 reals per atom (x,y,z,type), ref/atom.cpp:215-226
+template <class T>
+__global__ void border_unpack_kernel(Vec4<T>* __restrict__ x, int first, int n, const T* __restrict__ buf) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  Vec4<T> p;
+  p.x = buf[4 * k + 0];
+  p.y = buf[4 * k + 1];
+  p.z = buf[4 * k + 2];
+  p.w = type_to_lane<T>((int)buf[4 * k + 3]);
+  x[first + k] = p;
+}
+
+}  // namespace mmd

@@ -1,0 +1,1338 @@
+// C-ABI implementation (include/minimd_b200.h): the device context that owns all HBM state of
+// one rank and the launch logic behind every entry point.  sm_100a only; no CPU fallback --
+// without a CUDA device mmd_ctx_create fails with MMD_ERR_NODEVICE.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/minimd_b200.h"
+#include "common.cuh"
+#include "force_eam_kernels.cuh"
+#include "force_lj_kernels.cuh"
+#include "integrate_comm_kernels.cuh"
+#include "neighbor_kernels.cuh"
+#include "scan.cuh"
+
+#ifdef MMD_WITH_NCCL
+#include <nccl.h>
+#endif
+
+using namespace mmd;
+
+// ---------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return set_err(MMD_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, \
+                                          cudaGetErrorString(e_));                                 \
+  } while (0)
+#define MM(call)                  \
+  do {                            \
+    int r_ = (call);              \
+    if (r_ != MMD_OK) return r_;  \
+  } while (0)
+// kernel launch with accounting + immediate launch-error check (template kernels are passed
+// parenthesised: LAUNCH(c, (kernel<T, 1>), grid, block, args...))
+struct mmd_ctx;
+static int launch_fail(int line, cudaError_t e);
+template <class C, class K, class... Args>
+static inline int launch_impl(int line, C* ctx, K kern, int grid, int block, Args... args) {
+  if (grid <= 0) return MMD_OK;
+  kern<<<grid, block, 0, ctx->stream>>>(args...);
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return launch_fail(line, e);
+  return MMD_OK;
+}
+#define LAUNCH(ctx, kern, grid, block, ...) MM(launch_impl(__LINE__, ctx, kern, grid, block, __VA_ARGS__))
+
+#ifdef MMD_WITH_NCCL
+#define NC(call)                                                                                  \
+  do {                                                                                            \
+    ncclResult_t r_ = (call);                                                                     \
+    if (r_ != ncclSuccess) return set_err(MMD_ERR_NCCL, "%s:%d %s: %s", __FILE__, __LINE__, #call, \
+                                          ncclGetErrorString(r_));                                \
+  } while (0)
+#endif
+
+// ---------------------------------------------------------------------------------------
+// device buffer with geometric growth (optionally preserving contents)
+// ---------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t need, cudaStream_t s, size_t keep_bytes = 0, double slack = 1.0) {
+    if (need <= bytes) return MMD_OK;
+    size_t nb = (size_t)(need * slack) + 256;
+    void* q = nullptr;
+    CU(cudaMalloc(&q, nb));
+    if (p && keep_bytes) CU(cudaMemcpyAsync(q, p, std::min(keep_bytes, bytes), cudaMemcpyDeviceToDevice, s));
+    if (p) {
+      CU(cudaStreamSynchronize(s));
+      CU(cudaFree(p));
+    }
+    p = q;
+    bytes = nb;
+    return MMD_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class U> U* as() const { return reinterpret_cast<U*>(p); }
+};
+
+struct SwapState {
+  DevBuf list;  // Comm::sendlist[iswap]
+  int sendnum = 0, recvnum = 0, firstrecv = 0;
+};
+
+struct mmd_ctx {
+  int device = 0;
+  int prec = 8;  // sizeof(MMD_float)
+  int ntypes = 1;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  long long launches = 0;
+
+  // Atom
+  int nlocal = 0, nghost = 0;
+  int cap = 0;  // atoms the per-atom arrays can hold
+  DevBuf x, v, f, x_alt, v_alt;
+  double prd[3] = {0, 0, 0}, lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  bool have_box = false;
+  DevBuf stage_a, stage_b, stage_c, stage_i;  // host<->device AoS staging
+
+  // Neighbor
+  bool have_geo = false;
+  mmd_bin_geometry geo;
+  int mbins = 0;
+  std::vector<int> stencil;
+  int nruns = 0;
+  DevBuf runs, cutneighsq;
+  DevBuf atom_bin, bin_atoms, bincount, bin_start, cursor;
+  DevBuf tile_sums;
+  int binned_count = 0;  // atoms covered by the last binning
+  int max_bin_seen = 0;  // running max bin occupancy (drives the reference's atoms_per_bin)
+  DevBuf numneigh, neighbors;
+  int maxneighs = 100;  // Neighbor::maxneighs (ref/neighbor.cpp:48)
+  int neigh_stride = 104;
+  int neigh_rows = 0;
+  long long total_neigh = 0;
+  int neigh_builds = 0, neigh_resizes = 0;
+  int list_half = -1, list_gn = -1;
+
+  // Force
+  bool have_lj = false, lj_uniform = true;
+  DevBuf lj_cut, lj_s6, lj_eps;
+  double lj_cut0 = 0, lj_s60 = 0, lj_eps0 = 0;
+  int lj_tpa = 8;
+  bool have_eam = false, eam_uniform = true;
+  DevBuf eam_rho_val, eam_rho_der, eam_z2_val, eam_z2_der, eam_frho_val, eam_frho_der, eam_cut;
+  double eam_cut0 = 0, eam_rdr = 0, eam_rdrho = 0;
+  int eam_nr = 0, eam_nrho = 0;
+  int eam_tpa = 8;
+  DevBuf rho, fp;
+
+  // Comm
+  bool have_comm = false;
+  mmd_swap_table swaps;
+  SwapState sw[MMD_MAX_SWAPS];
+  DevBuf border_tiles;  // 2 arrays of tile counts
+  DevBuf sendbuf, recvbuf;
+#ifdef MMD_WITH_NCCL
+  ncclComm_t nccl = nullptr;
+#endif
+  int nranks = 1, rank = 0;
+
+  // device scalars + pinned mirror
+  // d_scal ints : [0] status, [1] max_n, [2] max_bin, [3] border total 0, [4] border total 1, [5] scan total
+  // d_ev doubles: [0] eng, [1] virial, [2] sum m v^2, [3] embed energy
+  int* d_scal = nullptr;
+  unsigned long long* d_total = nullptr;
+  double* d_ev = nullptr;
+  int* h_scal = nullptr;
+  unsigned long long* h_total = nullptr;
+  double* h_ev = nullptr;
+
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+static const int TPB = 256;
+static int launch_fail(int line, cudaError_t e) {
+  return set_err(MMD_ERR_CUDA, "mmd_device.cu:%d kernel launch: %s", line, cudaGetErrorString(e));
+}
+
+// ---------------------------------------------------------------------------------------
+// AoS(pad) <-> Vec4 conversion kernels (the only place the reference's host layout appears)
+// ---------------------------------------------------------------------------------------
+template <class T>
+__global__ void pack_x_kernel(const T* __restrict__ src, const int* __restrict__ type, int n, int pad,
+                              Vec4<T>* __restrict__ dst, int keep_type) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Vec4<T> p;
+  p.x = src[(size_t)i * pad + 0];
+  p.y = src[(size_t)i * pad + 1];
+  p.z = src[(size_t)i * pad + 2];
+  p.w = keep_type ? dst[i].w : type_to_lane<T>(type ? type[i] : 0);
+  dst[i] = p;
+}
+template <class T>
+__global__ void unpack_kernel(const Vec4<T>* __restrict__ src, int n, int pad, T* __restrict__ dst, int* __restrict__ type) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Vec4<T> p = src[i];
+  if (dst) {
+    dst[(size_t)i * pad + 0] = p.x;
+    dst[(size_t)i * pad + 1] = p.y;
+    dst[(size_t)i * pad + 2] = p.z;
+  }
+  if (type) type[i] = lane_to_type(p.w);
+}
+__global__ void rows_restride_kernel(const int* __restrict__ src, int rows, int src_stride, int dst_stride, int ncopy,
+                                     int* __restrict__ dst) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * ncopy) return;
+  const int r = (int)(idx / ncopy), k = (int)(idx % ncopy);
+  dst[(size_t)r * dst_stride + k] = src[(size_t)r * src_stride + k];
+}
+
+// ---------------------------------------------------------------------------------------
+// typed implementation
+// ---------------------------------------------------------------------------------------
+template <class T> struct Impl {
+  typedef Vec4<T> V;
+
+  static int reserve_atoms(mmd_ctx* c, int n) {
+    if (n <= c->cap) return MMD_OK;
+    int ncap = std::max((int)(n * 1.25) + 1024, c->cap);
+    const size_t keep = (size_t)(c->nlocal + c->nghost) * sizeof(V);
+    MM(c->x.reserve((size_t)ncap * sizeof(V), c->stream, keep));
+    MM(c->v.reserve((size_t)ncap * sizeof(V), c->stream, (size_t)c->nlocal * sizeof(V)));
+    MM(c->f.reserve((size_t)ncap * sizeof(V), c->stream, keep));
+    MM(c->x_alt.reserve((size_t)ncap * sizeof(V), c->stream));
+    MM(c->v_alt.reserve((size_t)ncap * sizeof(V), c->stream));
+    MM(c->atom_bin.reserve((size_t)ncap * sizeof(int), c->stream));
+    MM(c->bin_atoms.reserve((size_t)ncap * sizeof(int), c->stream));
+    if (c->have_eam) {
+      MM(c->rho.reserve((size_t)ncap * sizeof(T), c->stream));
+      MM(c->fp.reserve((size_t)ncap * sizeof(T), c->stream));
+    }
+    c->cap = ncap;
+    return MMD_OK;
+  }
+
+  // ---- Atom ----------------------------------------------------------------------------
+  static int upload(mmd_ctx* c, const void* x, const void* v, const int* type, int nlocal, int pad) {
+    c->nlocal = 0;
+    c->nghost = 0;
+    // ghost head-room estimate from the box: shell of thickness ~3 sigma around the sub-box
+    int guess = nlocal;
+    if (c->have_box) {
+      double vol = 1, shell = 1;
+      for (int d = 0; d < 3; d++) {
+        const double len = c->hi[d] - c->lo[d];
+        vol *= len;
+        shell *= len + 2 * 3.2 * (c->have_geo ? 1.0 / c->geo.bininvx : 1.0);
+      }
+      if (vol > 0) guess = (int)std::min(8.0 * nlocal + 4096, nlocal * (shell / vol));
+    }
+    MM(reserve_atoms(c, std::max(guess, nlocal)));
+    const size_t nb = (size_t)nlocal * pad * sizeof(T);
+    MM(c->stage_a.reserve(nb, c->stream));
+    MM(c->stage_b.reserve(nb, c->stream));
+    MM(c->stage_i.reserve((size_t)nlocal * sizeof(int), c->stream));
+    CU(cudaMemcpyAsync(c->stage_a.p, x, nb, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->stage_b.p, v, nb, cudaMemcpyHostToDevice, c->stream));
+    if (type) CU(cudaMemcpyAsync(c->stage_i.p, type, (size_t)nlocal * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    const int g = div_up(nlocal, TPB);
+    LAUNCH(c, pack_x_kernel<T>, g, TPB, c->stage_a.as<T>(), type ? c->stage_i.as<int>() : nullptr, nlocal, pad,
+           c->x.as<V>(), 0);
+    LAUNCH(c, pack_x_kernel<T>, g, TPB, c->stage_b.as<T>(), nullptr, nlocal, pad, c->v.as<V>(), 0);
+    CU(cudaMemsetAsync(c->f.p, 0, (size_t)c->cap * sizeof(V), c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->nlocal = nlocal;
+    c->neigh_rows = -1;  // lists and ghost tables refer to the previous atoms
+    for (int w = 0; w < MMD_MAX_SWAPS; w++) c->sw[w].sendnum = c->sw[w].recvnum = c->sw[w].firstrecv = 0;
+    return MMD_OK;
+  }
+
+  static int update(mmd_ctx* c, const void* x, const void* v, int first, int count, int pad) {
+    if (first < 0 || count < 0 || first + count > c->nlocal + c->nghost) return set_err(MMD_ERR_ARG, "update: range");
+    const size_t nb = (size_t)count * pad * sizeof(T);
+    const int g = div_up(count, TPB);
+    if (x) {
+      MM(c->stage_a.reserve(nb, c->stream));
+      CU(cudaMemcpyAsync(c->stage_a.p, x, nb, cudaMemcpyHostToDevice, c->stream));
+      LAUNCH(c, pack_x_kernel<T>, g, TPB, c->stage_a.as<T>(), nullptr, count, pad, c->x.as<V>() + first, 1);
+    }
+    if (v) {
+      if (first + count > c->nlocal) return set_err(MMD_ERR_ARG, "update: v is defined for local atoms only");
+      MM(c->stage_b.reserve(nb, c->stream));
+      CU(cudaMemcpyAsync(c->stage_b.p, v, nb, cudaMemcpyHostToDevice, c->stream));
+      LAUNCH(c, pack_x_kernel<T>, g, TPB, c->stage_b.as<T>(), nullptr, count, pad, c->v.as<V>() + first, 0);
+    }
+    return MMD_OK;
+  }
+
+  static int download(mmd_ctx* c, void* x, void* v, void* f, int* type, int first, int count, int pad) {
+    if (first < 0 || count < 0 || first + count > c->nlocal + c->nghost) return set_err(MMD_ERR_ARG, "download: range");
+    if (v && first + count > c->nlocal) return set_err(MMD_ERR_ARG, "download: v is defined for local atoms only");
+    if (count == 0) return MMD_OK;
+    const size_t nb = (size_t)count * pad * sizeof(T);
+    const int g = div_up(count, TPB);
+    if (x || type) {
+      MM(c->stage_a.reserve(nb, c->stream));
+      MM(c->stage_i.reserve((size_t)count * sizeof(int), c->stream));
+      if (pad > 3 && x) CU(cudaMemsetAsync(c->stage_a.p, 0, nb, c->stream));
+      LAUNCH(c, unpack_kernel<T>, g, TPB, c->x.as<V>() + first, count, pad, x ? c->stage_a.as<T>() : nullptr,
+             type ? c->stage_i.as<int>() : nullptr);
+      if (x) CU(cudaMemcpyAsync(x, c->stage_a.p, nb, cudaMemcpyDeviceToHost, c->stream));
+      if (type) CU(cudaMemcpyAsync(type, c->stage_i.p, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (v) {
+      MM(c->stage_b.reserve(nb, c->stream));
+      if (pad > 3) CU(cudaMemsetAsync(c->stage_b.p, 0, nb, c->stream));
+      LAUNCH(c, unpack_kernel<T>, g, TPB, c->v.as<V>() + first, count, pad, c->stage_b.as<T>(), nullptr);
+      CU(cudaMemcpyAsync(v, c->stage_b.p, nb, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (f) {
+      MM(c->stage_c.reserve(nb, c->stream));
+      if (pad > 3) CU(cudaMemsetAsync(c->stage_c.p, 0, nb, c->stream));
+      LAUNCH(c, unpack_kernel<T>, g, TPB, c->f.as<V>() + first, count, pad, c->stage_c.as<T>(), nullptr);
+      CU(cudaMemcpyAsync(f, c->stage_c.p, nb, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return MMD_OK;
+  }
+
+  static int pbc(mmd_ctx* c) {
+    if (!c->have_box) return set_err(MMD_ERR_STATE, "pbc: mmd_atom_set_box not called");
+    LAUNCH(c, pbc_kernel<T>, div_up(c->nlocal, TPB), TPB, c->x.as<V>(), c->nlocal, (T)c->prd[0], (T)c->prd[1],
+           (T)c->prd[2]);
+    return MMD_OK;
+  }
+
+  // ---- binning -------------------------------------------------------------------------
+  static BinGeo<T> geo(mmd_ctx* c) {
+    BinGeo<T> g;
+    for (int d = 0; d < 3; d++) g.prd[d] = (T)c->prd[d];
+    g.bininv[0] = (T)c->geo.bininvx; g.bininv[1] = (T)c->geo.bininvy; g.bininv[2] = (T)c->geo.bininvz;
+    g.nbin[0] = c->geo.nbinx; g.nbin[1] = c->geo.nbiny; g.nbin[2] = c->geo.nbinz;
+    g.mbin[0] = c->geo.mbinx; g.mbin[1] = c->geo.mbiny; g.mbin[2] = c->geo.mbinz;
+    g.mbinlo[0] = c->geo.mbinxlo; g.mbinlo[1] = c->geo.mbinylo; g.mbinlo[2] = c->geo.mbinzlo;
+    g.mbins = c->mbins;
+    return g;
+  }
+
+  // count -> exclusive scan -> fill -> per-bin sort.  All asynchronous.
+  static int binatoms_async(mmd_ctx* c, int n) {
+    if (!c->have_geo || !c->have_box) return set_err(MMD_ERR_STATE, "binatoms: mmd_neigh_setup / mmd_atom_set_box missing");
+    const int mb = c->mbins;
+    CU(cudaMemsetAsync(c->bincount.p, 0, (size_t)mb * sizeof(int), c->stream));
+    CU(cudaMemsetAsync(c->cursor.p, 0, (size_t)mb * sizeof(int), c->stream));
+    LAUNCH(c, bin_count_kernel<T>, div_up(n, TPB), TPB, c->x.as<V>(), n, geo(c), c->atom_bin.as<int>(),
+           c->bincount.as<int>(), c->d_scal + 0);
+    const int ntiles = div_up(mb, SCAN_TILE);
+    MM(c->tile_sums.reserve((size_t)ntiles * sizeof(int), c->stream));
+    LAUNCH(c, scan_tile_sums_kernel, ntiles, SCAN_THREADS, c->bincount.as<int>(), mb, c->tile_sums.as<int>(),
+           c->d_scal + 2);
+    LAUNCH(c, scan_spine_kernel, 1, 1024, c->tile_sums.as<int>(), ntiles, c->bin_start.as<int>() + mb, 0);
+    LAUNCH(c, scan_apply_kernel, ntiles, SCAN_THREADS, c->bincount.as<int>(), mb, c->tile_sums.as<int>(),
+           c->bin_start.as<int>());
+    LAUNCH(c, bin_fill_kernel, div_up(n, TPB), TPB, c->atom_bin.as<int>(), n, c->bin_start.as<int>(),
+           c->cursor.as<int>(), c->bin_atoms.as<int>());
+    LAUNCH(c, bin_sort_kernel, div_up(mb, TPB), TPB, c->bin_start.as<int>(), mb, c->bin_atoms.as<int>());
+    c->binned_count = n;
+    return MMD_OK;
+  }
+
+  static int read_status(mmd_ctx* c) {  // status + running max bin occupancy
+    CU(cudaMemcpyAsync(c->h_scal, c->d_scal, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->max_bin_seen = std::max(c->max_bin_seen, c->h_scal[2]);
+    if (c->h_scal[0] & 1) return set_err(MMD_ERR_STATE, "atom outside the bin grid (lost atom / bad coordinates)");
+    return MMD_OK;
+  }
+
+  static int sort(mmd_ctx* c) {
+    MM(binatoms_async(c, c->nlocal));
+    LAUNCH(c, permute_atoms_kernel<T>, div_up(c->nlocal, TPB), TPB, c->bin_atoms.as<int>(), c->nlocal, c->x.as<V>(),
+           c->v.as<V>(), c->x_alt.as<V>(), c->v_alt.as<V>());
+    std::swap(c->x, c->x_alt);  // pointer swap, ref/atom.cpp:409-418
+    std::swap(c->v, c->v_alt);
+    return MMD_OK;
+  }
+
+  // ---- neighbor build ------------------------------------------------------------------
+  static int build(mmd_ctx* c, int halfneigh, int gn, int* maxneighs_io, long long* total_out) {
+    if (maxneighs_io && *maxneighs_io > 0) c->maxneighs = *maxneighs_io;
+    const int nall = c->nlocal + c->nghost;
+    MM(binatoms_async(c, nall));
+    MM(c->numneigh.reserve((size_t)std::max(c->nlocal, 1) * sizeof(int), c->stream, 0, 1.1));
+    const int mode = halfneigh ? (gn ? 1 : 2) : 0;
+    for (;;) {
+      c->neigh_stride = (c->maxneighs + 7) & ~7;
+      MM(c->neighbors.reserve((size_t)std::max(c->nlocal, 1) * c->neigh_stride * sizeof(int), c->stream, 0, 1.05));
+      CU(cudaMemsetAsync(c->d_scal + 1, 0, sizeof(int), c->stream));
+      CU(cudaMemsetAsync(c->d_total, 0, sizeof(unsigned long long), c->stream));
+      const int grid = div_up(c->mbins, NB_WARPS);
+#define NB_ARGS                                                                                                  \
+  c->x.as<V>(), c->nlocal, c->bin_start.as<int>(), c->bin_atoms.as<int>(), c->mbins, c->runs.as<int2>(), c->nruns, \
+      c->cutneighsq.as<T>(), c->ntypes, c->neighbors.as<int>(), c->numneigh.as<int>(), c->neigh_stride,           \
+      c->d_scal + 1, c->d_total, c->maxneighs
+      if (mode == 0) LAUNCH(c, (neigh_build_kernel<T, 0>), grid, NB_WARPS * 32, NB_ARGS);
+      if (mode == 1) LAUNCH(c, (neigh_build_kernel<T, 1>), grid, NB_WARPS * 32, NB_ARGS);
+      if (mode == 2) LAUNCH(c, (neigh_build_kernel<T, 2>), grid, NB_WARPS * 32, NB_ARGS);
+#undef NB_ARGS
+      CU(cudaMemcpyAsync(c->h_total, c->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+      MM(read_status(c));
+      const int max_n = c->h_scal[1];
+      if (max_n >= c->maxneighs) {  // ref/neighbor.cpp:186-208
+        c->maxneighs = (int)(max_n * 1.2);
+        c->neigh_resizes++;
+        continue;
+      }
+      break;
+    }
+    c->total_neigh = (long long)*c->h_total;
+    c->neigh_rows = c->nlocal;
+    c->neigh_builds++;
+    c->list_half = halfneigh;
+    c->list_gn = gn;
+    if (maxneighs_io) *maxneighs_io = c->maxneighs;
+    if (total_out) *total_out = c->total_neigh;
+    return MMD_OK;
+  }
+
+  // ---- LJ ------------------------------------------------------------------------------
+  template <int TPA, int HALF, int GN, int EV>
+  static int lj_launch(mmd_ctx* c) {
+    LJParams<T> P;
+    P.cutforcesq = (T)c->lj_cut0; P.sigma6 = (T)c->lj_s60; P.epsilon = (T)c->lj_eps0;
+    P.cutforcesq_tab = c->lj_cut.as<T>(); P.sigma6_tab = c->lj_s6.as<T>(); P.epsilon_tab = c->lj_eps.as<T>();
+    P.ntypes = c->ntypes;
+    const int grid = div_up((long long)c->nlocal * TPA, LJ_BLOCK);
+    if (c->lj_uniform)
+      LAUNCH(c, (force_lj_kernel<T, TPA, HALF, GN, EV, 1>), grid, LJ_BLOCK, c->x.as<V>(), c->f.as<V>(),
+             c->neighbors.as<int>(), c->numneigh.as<int>(), c->neigh_stride, c->nlocal, P, c->d_ev);
+    else
+      LAUNCH(c, (force_lj_kernel<T, TPA, HALF, GN, EV, 0>), grid, LJ_BLOCK, c->x.as<V>(), c->f.as<V>(),
+             c->neighbors.as<int>(), c->numneigh.as<int>(), c->neigh_stride, c->nlocal, P, c->d_ev);
+    return MMD_OK;
+  }
+  template <int TPA> static int lj_dispatch(mmd_ctx* c, int half, int gn, int ev) {
+    if (half) {
+      if (gn) return ev ? lj_launch<TPA, 1, 1, 1>(c) : lj_launch<TPA, 1, 1, 0>(c);
+      return ev ? lj_launch<TPA, 1, 0, 1>(c) : lj_launch<TPA, 1, 0, 0>(c);
+    }
+    return ev ? lj_launch<TPA, 0, 0, 1>(c) : lj_launch<TPA, 0, 0, 0>(c);
+  }
+  // clear_f: zero f[0,nall) first (half lists; skipped by mmd_run when a fused prologue did it)
+  static int lj_async(mmd_ctx* c, int half, int gn, int ev, bool clear_f) {
+    if (!c->have_lj) return set_err(MMD_ERR_STATE, "force_lj: mmd_force_lj_setup missing");
+    if (c->neigh_rows != c->nlocal) return set_err(MMD_ERR_STATE, "force_lj: neighbor list is stale (build first)");
+    if (half && clear_f) CU(cudaMemsetAsync(c->f.p, 0, (size_t)(c->nlocal + c->nghost) * sizeof(V), c->stream));
+    if (ev) CU(cudaMemsetAsync(c->d_ev, 0, 2 * sizeof(double), c->stream));
+    switch (c->lj_tpa) {
+      case 1: return lj_dispatch<1>(c, half, gn, ev);
+      case 2: return lj_dispatch<2>(c, half, gn, ev);
+      case 4: return lj_dispatch<4>(c, half, gn, ev);
+      case 8: return lj_dispatch<8>(c, half, gn, ev);
+      case 16: return lj_dispatch<16>(c, half, gn, ev);
+      default: return lj_dispatch<32>(c, half, gn, ev);
+    }
+  }
+  static int read_ev(mmd_ctx* c, int n) {
+    CU(cudaMemcpyAsync(c->h_ev, c->d_ev, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return MMD_OK;
+  }
+
+  // ---- EAM -----------------------------------------------------------------------------
+  static EAMTables<T> eam_tables(mmd_ctx* c) {
+    EAMTables<T> E;
+    E.rho_val = c->eam_rho_val.as<V>(); E.rho_der = c->eam_rho_der.as<V>();
+    E.z2_val = c->eam_z2_val.as<V>(); E.z2_der = c->eam_z2_der.as<V>();
+    E.frho_val = c->eam_frho_val.as<V>(); E.frho_der = c->eam_frho_der.as<V>();
+    E.cutforcesq_tab = c->eam_cut.as<T>();
+    E.cutforcesq = (T)c->eam_cut0;
+    E.rdr = (T)c->eam_rdr; E.rdrho = (T)c->eam_rdrho;
+    E.nr = c->eam_nr; E.nrho = c->eam_nrho; E.ntypes = c->ntypes;
+    return E;
+  }
+  static int eam_setup(mmd_ctx* c, const void* rhor, const void* z2r, const void* frho, int nr, int nrho, int nr_tot,
+                       int nrho_tot, double rdr, double rdrho, const void* cutsq) {
+    const int nn = c->ntypes * c->ntypes;
+    const T* hr = (const T*)rhor; const T* hz = (const T*)z2r; const T* hf = (const T*)frho; const T* hc = (const T*)cutsq;
+    bool uni = true;
+    for (int t = 1; t < nn && uni; t++) {
+      uni = uni && !memcmp(hr, hr + (size_t)t * nr_tot, sizeof(T) * (size_t)(nr + 1) * 7) &&
+            !memcmp(hz, hz + (size_t)t * nr_tot, sizeof(T) * (size_t)(nr + 1) * 7) &&
+            !memcmp(hf, hf + (size_t)t * nrho_tot, sizeof(T) * (size_t)(nrho + 1) * 7) && hc[t] == hc[0];
+    }
+    c->eam_uniform = uni;
+    auto repack = [&](const T* src, int n, int tot, int off, int cnt, DevBuf& dst) -> int {
+      std::vector<V> h((size_t)nn * (n + 1));
+      for (int t = 0; t < nn; t++)
+        for (int m = 0; m <= n; m++) {
+          V r; r.x = r.y = r.z = r.w = (T)0;
+          const T* s = src + (size_t)t * tot + (size_t)m * 7 + off;
+          r.x = s[0]; r.y = s[1]; r.z = s[2];
+          if (cnt == 4) r.w = s[3];
+          h[(size_t)t * (n + 1) + m] = r;
+        }
+      MM(dst.reserve(h.size() * sizeof(V), c->stream));
+      CU(cudaMemcpyAsync(dst.p, h.data(), h.size() * sizeof(V), cudaMemcpyHostToDevice, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      return MMD_OK;
+    };
+    MM(repack(hr, nr, nr_tot, 3, 4, c->eam_rho_val));
+    MM(repack(hr, nr, nr_tot, 0, 3, c->eam_rho_der));
+    MM(repack(hz, nr, nr_tot, 3, 4, c->eam_z2_val));
+    MM(repack(hz, nr, nr_tot, 0, 3, c->eam_z2_der));
+    MM(repack(hf, nrho, nrho_tot, 3, 4, c->eam_frho_val));
+    MM(repack(hf, nrho, nrho_tot, 0, 3, c->eam_frho_der));
+    MM(c->eam_cut.reserve((size_t)nn * sizeof(T), c->stream));
+    CU(cudaMemcpy(c->eam_cut.p, hc, (size_t)nn * sizeof(T), cudaMemcpyHostToDevice));
+    c->eam_cut0 = (double)hc[0];
+    c->eam_rdr = rdr; c->eam_rdrho = rdrho; c->eam_nr = nr; c->eam_nrho = nrho;
+    c->have_eam = true;
+    if (c->cap > 0) {
+      MM(c->rho.reserve((size_t)c->cap * sizeof(T), c->stream));
+      MM(c->fp.reserve((size_t)c->cap * sizeof(T), c->stream));
+    }
+    return MMD_OK;
+  }
+
+  template <int TPA, int EV, int UNI> static int eam_launch(mmd_ctx* c, int half) {
+    const EAMTables<T> E = eam_tables(c);
+    const int grid = div_up((long long)c->nlocal * TPA, EAM_BLOCK);
+    const int nall = c->nlocal + c->nghost;
+#define EAM_RHO_ARGS c->x.as<V>(), c->neighbors.as<int>(), c->numneigh.as<int>(), c->neigh_stride, c->nlocal, E, \
+                     c->rho.as<T>(), c->fp.as<T>(), c->d_ev + 3
+#define EAM_PAIR_ARGS c->x.as<V>(), c->f.as<V>(), c->neighbors.as<int>(), c->numneigh.as<int>(), c->neigh_stride, \
+                      c->nlocal, E, c->fp.as<T>(), c->d_ev
+    if (half) {
+      CU(cudaMemsetAsync(c->f.p, 0, (size_t)nall * sizeof(V), c->stream));
+      CU(cudaMemsetAsync(c->rho.p, 0, (size_t)c->nlocal * sizeof(T), c->stream));
+      LAUNCH(c, (eam_rho_kernel<T, TPA, 0, EV, UNI>), grid, EAM_BLOCK, EAM_RHO_ARGS);
+      LAUNCH(c, (eam_embed_kernel<T, EV, UNI>), div_up(c->nlocal, TPB), TPB, c->x.as<V>(), c->nlocal, E, c->rho.as<T>(),
+             c->fp.as<T>(), c->d_ev + 3);
+    } else {
+      LAUNCH(c, (eam_rho_kernel<T, TPA, 1, EV, UNI>), grid, EAM_BLOCK, EAM_RHO_ARGS);
+    }
+    MM(forward_scalar(c, c->fp.as<T>()));
+    if (half) LAUNCH(c, (eam_pair_kernel<T, TPA, 1, EV, UNI>), grid, EAM_BLOCK, EAM_PAIR_ARGS);
+    else LAUNCH(c, (eam_pair_kernel<T, TPA, 0, EV, UNI>), grid, EAM_BLOCK, EAM_PAIR_ARGS);
+#undef EAM_RHO_ARGS
+#undef EAM_PAIR_ARGS
+    return MMD_OK;
+  }
+  template <int TPA> static int eam_dispatch(mmd_ctx* c, int half, int ev) {
+    if (c->eam_uniform) return ev ? eam_launch<TPA, 1, 1>(c, half) : eam_launch<TPA, 0, 1>(c, half);
+    return ev ? eam_launch<TPA, 1, 0>(c, half) : eam_launch<TPA, 0, 0>(c, half);
+  }
+  static int eam_async(mmd_ctx* c, int half, int ev) {
+    if (!c->have_eam) return set_err(MMD_ERR_STATE, "force_eam: mmd_force_eam_setup missing");
+    if (c->neigh_rows != c->nlocal) return set_err(MMD_ERR_STATE, "force_eam: neighbor list is stale (build first)");
+    MM(c->rho.reserve((size_t)c->cap * sizeof(T), c->stream));
+    MM(c->fp.reserve((size_t)c->cap * sizeof(T), c->stream));
+    if (ev) CU(cudaMemsetAsync(c->d_ev, 0, 4 * sizeof(double), c->stream));
+    switch (c->eam_tpa) {
+      case 1: return eam_dispatch<1>(c, half, ev);
+      case 2: return eam_dispatch<2>(c, half, ev);
+      case 4: return eam_dispatch<4>(c, half, ev);
+      case 8: return eam_dispatch<8>(c, half, ev);
+      case 16: return eam_dispatch<16>(c, half, ev);
+      default: return eam_dispatch<32>(c, half, ev);
+    }
+  }
+  // eng_vdwl from the device partial sums (see eam_pair_kernel): full = 2*(embed + sum 0.5 phi),
+  // half = embed + sum phi
+  static double eam_energy(mmd_ctx* c, int half) { return half ? c->h_ev[3] + c->h_ev[0] : 2.0 * (c->h_ev[3] + c->h_ev[0]); }
+
+  // ---- integrate -----------------------------------------------------------------------
+  static int initial(mmd_ctx* c, double dt, double dtforce, bool zero_f) {
+    const int g = div_up(c->nlocal, TPB);
+    if (zero_f) LAUNCH(c, (initial_integrate_kernel<T, 1>), g, TPB, c->x.as<V>(), c->v.as<V>(), c->f.as<V>(), c->nlocal, (T)dt, (T)dtforce);
+    else LAUNCH(c, (initial_integrate_kernel<T, 0>), g, TPB, c->x.as<V>(), c->v.as<V>(), c->f.as<V>(), c->nlocal, (T)dt, (T)dtforce);
+    return MMD_OK;
+  }
+  static int final_(mmd_ctx* c, double dtforce, bool ke, double mass) {
+    const int g = div_up(c->nlocal, TPB);
+    if (ke) {
+      CU(cudaMemsetAsync(c->d_ev + 2, 0, sizeof(double), c->stream));
+      LAUNCH(c, (final_integrate_kernel<T, 1>), g, TPB, c->v.as<V>(), c->f.as<V>(), c->nlocal, (T)dtforce, (T)mass, c->d_ev + 2);
+    } else {
+      LAUNCH(c, (final_integrate_kernel<T, 0>), g, TPB, c->v.as<V>(), c->f.as<V>(), c->nlocal, (T)dtforce, (T)mass, c->d_ev + 2);
+    }
+    return MMD_OK;
+  }
+  static int sum_mv2(mmd_ctx* c, double mass, double* out) {
+    CU(cudaMemsetAsync(c->d_ev + 2, 0, sizeof(double), c->stream));
+    const int g = std::max(1, std::min(div_up(c->nlocal, TPB), 148 * 8));
+    LAUNCH(c, sum_mv2_kernel<T>, g, TPB, c->v.as<V>(), c->nlocal, (T)mass, c->d_ev + 2);
+    MM(read_ev(c, 3));
+    *out = c->h_ev[2];
+    return MMD_OK;
+  }
+
+  // ---- Comm ----------------------------------------------------------------------------
+  static SwapPairDev pair_desc(mmd_ctx* c, int w0, int nsw) {
+    SwapPairDev sp;
+    memset(&sp, 0, sizeof sp);
+    for (int s = 0; s < nsw; s++) {
+      const int w = w0 + s;
+      sp.list[s] = c->sw[w].list.as<int>();
+      sp.count[s] = c->sw[w].sendnum;
+      sp.first[s] = c->sw[w].firstrecv;
+      sp.any[s] = c->swaps.pbc_any[w];
+      sp.flag[s][0] = c->swaps.pbc_flagx[w];
+      sp.flag[s][1] = c->swaps.pbc_flagy[w];
+      sp.flag[s][2] = c->swaps.pbc_flagz[w];
+    }
+    return sp;
+  }
+  static bool is_self(mmd_ctx* c, int w) { return c->swaps.sendproc[w] == c->swaps.me; }
+
+#ifdef MMD_WITH_NCCL
+  static ncclDataType_t nccl_real() { return sizeof(T) == 8 ? ncclDouble : ncclFloat; }
+  // one grouped send+recv (MPI_Sendrecv of ref/comm.cpp:304-306)
+  static int sendrecv(mmd_ctx* c, const void* sbuf, size_t scount, int dst, void* rbuf, size_t rcount, int src,
+                      ncclDataType_t dt) {
+    if (!c->nccl) return set_err(MMD_ERR_STATE, "remote swap requested but mmd_comm_nccl_init was not called");
+    NC(ncclGroupStart());
+    if (scount) NC(ncclSend(sbuf, scount, dt, dst, c->nccl, c->stream));
+    if (rcount) NC(ncclRecv(rbuf, rcount, dt, src, c->nccl, c->stream));
+    NC(ncclGroupEnd());
+    return MMD_OK;
+  }
+#endif
+
+  static int communicate(mmd_ctx* c, bool zero_ghost_f) {
+    if (!c->have_comm) return set_err(MMD_ERR_STATE, "communicate: mmd_comm_setup missing");
+    const T px = (T)c->prd[0], py = (T)c->prd[1], pz = (T)c->prd[2];
+    for (int w = 0; w < c->swaps.nswap; w += 2) {
+      const int nsw = std::min(2, c->swaps.nswap - w);
+      if (is_self(c, w) && (nsw < 2 || is_self(c, w + 1))) {
+        const SwapPairDev sp = pair_desc(c, w, nsw);
+        const int n = sp.count[0] + sp.count[1];
+        if (zero_ghost_f) LAUNCH(c, (halo_forward_self_kernel<T, 1>), div_up(n, TPB), TPB, c->x.as<V>(), c->f.as<V>(), sp, px, py, pz);
+        else LAUNCH(c, (halo_forward_self_kernel<T, 0>), div_up(n, TPB), TPB, c->x.as<V>(), c->f.as<V>(), sp, px, py, pz);
+      } else {
+#ifdef MMD_WITH_NCCL
+        for (int s = 0; s < nsw; s++) {
+          const int ww = w + s;
+          const int ns = c->sw[ww].sendnum, nr = c->sw[ww].recvnum;
+          MM(c->sendbuf.reserve((size_t)3 * ns * sizeof(T), c->stream, 0, 1.5));
+          MM(c->recvbuf.reserve((size_t)3 * nr * sizeof(T), c->stream, 0, 1.5));
+          LAUNCH(c, halo_pack_x_kernel<T>, div_up(ns, TPB), TPB, c->x.as<V>(), c->sw[ww].list.as<int>(), ns,
+                 c->swaps.pbc_any[ww], c->swaps.pbc_flagx[ww], c->swaps.pbc_flagy[ww], c->swaps.pbc_flagz[ww], px, py, pz,
+                 c->sendbuf.as<T>());
+          MM(sendrecv(c, c->sendbuf.p, (size_t)3 * ns, c->swaps.sendproc[ww], c->recvbuf.p, (size_t)3 * nr,
+                      c->swaps.recvproc[ww], nccl_real()));
+          if (zero_ghost_f) LAUNCH(c, (halo_unpack_x_kernel<T, 1>), div_up(nr, TPB), TPB, c->x.as<V>(), c->f.as<V>(), c->sw[ww].firstrecv, nr, c->recvbuf.as<T>());
+          else LAUNCH(c, (halo_unpack_x_kernel<T, 0>), div_up(nr, TPB), TPB, c->x.as<V>(), c->f.as<V>(), c->sw[ww].firstrecv, nr, c->recvbuf.as<T>());
+        }
+#else
+        return set_err(MMD_ERR_STATE, "remote swap but library built without NCCL");
+#endif
+      }
+    }
+    return MMD_OK;
+  }
+
+  static int reverse(mmd_ctx* c) {
+    if (!c->have_comm) return set_err(MMD_ERR_STATE, "reverse_communicate: mmd_comm_setup missing");
+    const int npairs = (c->swaps.nswap + 1) / 2;
+    for (int p = npairs - 1; p >= 0; p--) {
+      const int w = 2 * p;
+      const int nsw = std::min(2, c->swaps.nswap - w);
+      if (is_self(c, w) && (nsw < 2 || is_self(c, w + 1))) {
+        const SwapPairDev sp = pair_desc(c, w, nsw);
+        LAUNCH(c, halo_reverse_self_kernel<T>, div_up(sp.count[0] + sp.count[1], TPB), TPB, c->f.as<V>(), sp);
+      } else {
+#ifdef MMD_WITH_NCCL
+        for (int s = nsw - 1; s >= 0; s--) {
+          const int ww = w + s;
+          const int ns = c->sw[ww].sendnum, nr = c->sw[ww].recvnum;
+          MM(c->sendbuf.reserve((size_t)3 * nr * sizeof(T), c->stream, 0, 1.5));
+          MM(c->recvbuf.reserve((size_t)3 * ns * sizeof(T), c->stream, 0, 1.5));
+          LAUNCH(c, halo_pack_f_kernel<T>, div_up(nr, TPB), TPB, c->f.as<V>(), c->sw[ww].firstrecv, nr, c->sendbuf.as<T>());
+          MM(sendrecv(c, c->sendbuf.p, (size_t)3 * nr, c->swaps.recvproc[ww], c->recvbuf.p, (size_t)3 * ns,
+                      c->swaps.sendproc[ww], nccl_real()));
+          LAUNCH(c, halo_unpack_f_kernel<T>, div_up(ns, TPB), TPB, c->f.as<V>(), c->sw[ww].list.as<int>(), ns, c->recvbuf.as<T>());
+        }
+#else
+        return set_err(MMD_ERR_STATE, "remote swap but library built without NCCL");
+#endif
+      }
+    }
+    return MMD_OK;
+  }
+
+  // forward halo of one scalar per atom (EAM fp)
+  static int forward_scalar(mmd_ctx* c, T* a) {
+    if (!c->have_comm) return set_err(MMD_ERR_STATE, "mmd_comm_setup missing");
+    for (int w = 0; w < c->swaps.nswap; w += 2) {
+      const int nsw = std::min(2, c->swaps.nswap - w);
+      if (is_self(c, w) && (nsw < 2 || is_self(c, w + 1))) {
+        const SwapPairDev sp = pair_desc(c, w, nsw);
+        LAUNCH(c, halo_forward_scalar_self_kernel<T>, div_up(sp.count[0] + sp.count[1], TPB), TPB, a, sp);
+      } else {
+#ifdef MMD_WITH_NCCL
+        for (int s = 0; s < nsw; s++) {
+          const int ww = w + s;
+          const int ns = c->sw[ww].sendnum, nr = c->sw[ww].recvnum;
+          MM(c->sendbuf.reserve((size_t)ns * sizeof(T), c->stream, 0, 1.5));
+          LAUNCH(c, gather_scalar_kernel<T>, div_up(ns, TPB), TPB, a, c->sw[ww].list.as<int>(), ns, c->sendbuf.as<T>());
+          MM(sendrecv(c, c->sendbuf.p, (size_t)ns, c->swaps.sendproc[ww], a + c->sw[ww].firstrecv, (size_t)nr,
+                      c->swaps.recvproc[ww], nccl_real()));
+        }
+#else
+        return set_err(MMD_ERR_STATE, "remote swap but library built without NCCL");
+#endif
+      }
+    }
+    return MMD_OK;
+  }
+
+  // Comm::borders.  Per swap pair: count -> spine -> (host reads the two totals, grows arrays)
+  // -> ordered scatter that writes the send lists and, for self swaps, the ghosts themselves.
+  static int borders(mmd_ctx* c) {
+    if (!c->have_comm || !c->have_box) return set_err(MMD_ERR_STATE, "borders: mmd_comm_setup / mmd_atom_set_box missing");
+    c->nghost = 0;
+    const T px = (T)c->prd[0], py = (T)c->prd[1], pz = (T)c->prd[2];
+    int w = 0;
+    for (int dim = 0; dim < 3; dim++) {
+      int nfirst = 0, nlast = 0;
+      for (int layer = 0; layer < c->swaps.need[dim]; layer++, w += 2) {
+        nfirst = nlast;
+        nlast = c->nlocal + c->nghost;
+        const int nscan = nlast - nfirst;
+        const int ntiles = std::max(1, div_up(nscan, BORDER_THREADS));
+        MM(c->border_tiles.reserve((size_t)2 * ntiles * sizeof(int), c->stream, 0, 1.2));
+        int* t0 = c->border_tiles.as<int>();
+        int* t1 = t0 + ntiles;
+        const T lo0 = (T)c->swaps.slablo[w], hi0 = (T)c->swaps.slabhi[w];
+        const T lo1 = (T)c->swaps.slablo[w + 1], hi1 = (T)c->swaps.slabhi[w + 1];
+        LAUNCH(c, border_count_kernel<T>, ntiles, BORDER_THREADS, c->x.as<V>(), nfirst, nlast, dim, lo0, hi0, lo1, hi1, t0, t1);
+        LAUNCH(c, scan_spine_kernel, 2, 1024, t0, ntiles, c->d_scal + 3, ntiles);
+        CU(cudaMemcpyAsync(c->h_scal + 3, c->d_scal + 3, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        const int ns0 = c->h_scal[3], ns1 = c->h_scal[4];
+        MM(c->sw[w].list.reserve((size_t)std::max(ns0, 1) * sizeof(int), c->stream, 0, 1.5));
+        MM(c->sw[w + 1].list.reserve((size_t)std::max(ns1, 1) * sizeof(int), c->stream, 0, 1.5));
+        const bool self0 = is_self(c, w), self1 = is_self(c, w + 1);
+        int nr0 = ns0, nr1 = ns1;
+        T *b0 = nullptr, *b1 = nullptr;
+        if (!self0 || !self1) {
+#ifdef MMD_WITH_NCCL
+          MM(c->sendbuf.reserve((size_t)4 * (ns0 + ns1) * sizeof(T), c->stream, 0, 1.5));
+          b0 = c->sendbuf.as<T>();
+          b1 = b0 + (size_t)4 * ns0;
+          // counts first (ref/comm.cpp:822-824); ints travel through the pinned/host path via NCCL int buffers
+          int* d_cnt = c->d_scal + 6;  // [6],[7] send counts, [8],[9] recv counts
+          c->h_scal[6] = ns0; c->h_scal[7] = ns1;
+          CU(cudaMemcpyAsync(d_cnt, c->h_scal + 6, 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+          if (!c->nccl) return set_err(MMD_ERR_STATE, "remote swap requested but mmd_comm_nccl_init was not called");
+          NC(ncclGroupStart());
+          if (!self0) { NC(ncclSend(d_cnt + 0, 1, ncclInt, c->swaps.sendproc[w], c->nccl, c->stream));
+                        NC(ncclRecv(d_cnt + 2, 1, ncclInt, c->swaps.recvproc[w], c->nccl, c->stream)); }
+          if (!self1) { NC(ncclSend(d_cnt + 1, 1, ncclInt, c->swaps.sendproc[w + 1], c->nccl, c->stream));
+                        NC(ncclRecv(d_cnt + 3, 1, ncclInt, c->swaps.recvproc[w + 1], c->nccl, c->stream)); }
+          NC(ncclGroupEnd());
+          CU(cudaMemcpyAsync(c->h_scal + 8, d_cnt + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+          CU(cudaStreamSynchronize(c->stream));
+          if (!self0) nr0 = c->h_scal[8];
+          if (!self1) nr1 = c->h_scal[9];
+#else
+          return set_err(MMD_ERR_STATE, "remote swap but library built without NCCL");
+#endif
+        }
+        const int first0 = c->nlocal + c->nghost, first1 = first0 + nr0;
+        MM(reserve_atoms(c, first1 + nr1));
+        SwapPairDev sp = pair_desc(c, w, 2);
+        LAUNCH(c, border_scatter_kernel<T>, ntiles, BORDER_THREADS, c->x.as<V>(), nfirst, nlast, dim, lo0, hi0, lo1, hi1,
+               t0, t1, c->sw[w].list.as<int>(), c->sw[w + 1].list.as<int>(), (int)self0, (int)self1, first0, first1, sp,
+               px, py, pz, b0, b1);
+#ifdef MMD_WITH_NCCL
+        if (!self0 || !self1) {
+          MM(c->recvbuf.reserve((size_t)4 * (nr0 + nr1) * sizeof(T), c->stream, 0, 1.5));
+          T* r0 = c->recvbuf.as<T>();
+          T* r1 = r0 + (size_t)4 * nr0;
+          NC(ncclGroupStart());
+          if (!self0) { if (ns0) NC(ncclSend(b0, (size_t)4 * ns0, nccl_real(), c->swaps.sendproc[w], c->nccl, c->stream));
+                        if (nr0) NC(ncclRecv(r0, (size_t)4 * nr0, nccl_real(), c->swaps.recvproc[w], c->nccl, c->stream)); }
+          if (!self1) { if (ns1) NC(ncclSend(b1, (size_t)4 * ns1, nccl_real(), c->swaps.sendproc[w + 1], c->nccl, c->stream));
+                        if (nr1) NC(ncclRecv(r1, (size_t)4 * nr1, nccl_real(), c->swaps.recvproc[w + 1], c->nccl, c->stream)); }
+          NC(ncclGroupEnd());
+          if (!self0) LAUNCH(c, border_unpack_kernel<T>, div_up(nr0, TPB), TPB, c->x.as<V>(), first0, nr0, r0);
+          if (!self1) LAUNCH(c, border_unpack_kernel<T>, div_up(nr1, TPB), TPB, c->x.as<V>(), first1, nr1, r1);
+        }
+#endif
+        c->sw[w].sendnum = ns0; c->sw[w].recvnum = nr0; c->sw[w].firstrecv = first0;
+        c->sw[w + 1].sendnum = ns1; c->sw[w + 1].recvnum = nr1; c->sw[w + 1].firstrecv = first1;
+        c->nghost += nr0 + nr1;
+      }
+    }
+    c->neigh_rows = -1;  // lists are stale until the next build
+    return MMD_OK;
+  }
+
+  // ---- fused time loop -------------------------------------------------------------------
+  static int run(mmd_ctx* c, const mmd_run_params* p, mmd_thermo_sample* samples, int max_samples, int* nsamples,
+                 float* elapsed_ms) {
+    int ns = 0;
+    int next_sort = p->sort_every > 0 ? p->sort_every : p->total_steps + 1;
+    while (p->sort_every > 0 && next_sort <= p->first_step) next_sort += p->sort_every;
+    const bool reverse_needed = p->halfneigh && p->ghost_newton;
+    if (elapsed_ms) CU(cudaEventRecord(c->ev0, c->stream));
+    for (int n = p->first_step; n < p->first_step + p->ntimes; n++) {
+      MM(initial(c, p->dt, p->dtforce, false));
+      if ((n + 1) % p->neigh_every) {
+        MM(communicate(c, false));
+      } else {
+        MM(exchange(c));
+        if (n + 1 >= next_sort) {
+          MM(sort(c));
+          next_sort += p->sort_every;
+        }
+        MM(borders(c));
+        int mx = c->maxneighs;
+        MM(build(c, p->halfneigh, p->ghost_newton, &mx, nullptr));
+      }
+      const int ev = p->thermo_nstat > 0 ? ((n + 1) % p->thermo_nstat == 0) : 0;
+      if (p->force_style == 0) MM(lj_async(c, p->halfneigh, p->ghost_newton, ev, true));
+      else MM(eam_async(c, p->halfneigh, ev));
+      if (reverse_needed) MM(reverse(c));
+      MM(final_(c, p->dtforce, ev != 0, p->mass));
+      if (ev) {
+        MM(read_ev(c, 4));
+        if (ns < max_samples && samples) {
+          samples[ns].step = n + 1;
+          samples[ns].sum_mv2 = c->h_ev[2];
+          samples[ns].eng_vdwl = p->force_style == 0 ? c->h_ev[0] : eam_energy(c, p->halfneigh);
+          samples[ns].virial = c->h_ev[1];
+        }
+        ns++;
+      }
+    }
+    if (elapsed_ms) {
+      CU(cudaEventRecord(c->ev1, c->stream));
+      CU(cudaEventSynchronize(c->ev1));
+      CU(cudaEventElapsedTime(elapsed_ms, c->ev0, c->ev1));
+    }
+    if (nsamples) *nsamples = ns;
+    return MMD_OK;
+  }
+
+  static int exchange(mmd_ctx* c) {
+    MM(pbc(c));
+    for (int d = 0; d < 3; d++)
+      if (c->swaps.procgrid[d] > 1) return set_err(MMD_ERR_STATE, "exchange across ranks is not implemented yet");
+    return MMD_OK;
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// extern "C" surface
+// ---------------------------------------------------------------------------------------
+#define DISPATCH(ctx, expr_d, expr_f) ((ctx)->prec == 8 ? (expr_d) : (expr_f))
+#define CHECK_CTX(ctx)                                           \
+  do {                                                           \
+    if (!(ctx)) return set_err(MMD_ERR_ARG, "null context");     \
+    cudaError_t e_ = cudaSetDevice((ctx)->device);               \
+    if (e_ != cudaSuccess) return set_err(MMD_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e_)); \
+  } while (0)
+
+template <class T> static bool all_equal(const T* a, int n) {
+  for (int i = 1; i < n; i++)
+    if (a[i] != a[0]) return false;
+  return true;
+}
+
+extern "C" {
+
+const char* mmd_last_error(void) { return g_err; }
+int mmd_abi_version(void) { return MMD_ABI_VERSION; }
+int mmd_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int mmd_ctx_create(int device, int precision_bytes, int ntypes, void* stream, mmd_ctx** out) {
+  if (!out) return set_err(MMD_ERR_ARG, "out is null");
+  *out = nullptr;
+  if (precision_bytes != 4 && precision_bytes != 8) return set_err(MMD_ERR_ARG, "precision_bytes must be 4 or 8");
+  if (ntypes < 1) return set_err(MMD_ERR_ARG, "ntypes must be >= 1");
+  int ndev = mmd_device_count();
+  if (ndev <= 0) return set_err(MMD_ERR_NODEVICE, "no CUDA device visible: minimd_b200 has no CPU path");
+  if (device < 0 || device >= ndev) return set_err(MMD_ERR_ARG, "device %d out of range (%d visible)", device, ndev);
+  CU(cudaSetDevice(device));
+  mmd_ctx* c = new mmd_ctx();
+  c->device = device;
+  c->prec = precision_bytes;
+  c->ntypes = ntypes;
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+  } else {
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  CU(cudaMalloc(&c->d_scal, 16 * sizeof(int)));
+  CU(cudaMalloc(&c->d_total, sizeof(unsigned long long)));
+  CU(cudaMalloc(&c->d_ev, 4 * sizeof(double)));
+  CU(cudaMemset(c->d_scal, 0, 16 * sizeof(int)));
+  CU(cudaMemset(c->d_total, 0, sizeof(unsigned long long)));
+  CU(cudaMemset(c->d_ev, 0, 4 * sizeof(double)));
+  CU(cudaMallocHost(&c->h_scal, 16 * sizeof(int)));
+  CU(cudaMallocHost(&c->h_total, sizeof(unsigned long long)));
+  CU(cudaMallocHost(&c->h_ev, 4 * sizeof(double)));
+  memset(c->h_scal, 0, 16 * sizeof(int));
+  CU(cudaEventCreate(&c->ev0));
+  CU(cudaEventCreate(&c->ev1));
+  memset(&c->swaps, 0, sizeof c->swaps);
+  *out = c;
+  return MMD_OK;
+}
+
+int mmd_ctx_destroy(mmd_ctx* c) {
+  if (!c) return MMD_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  DevBuf* bufs[] = {&c->x, &c->v, &c->f, &c->x_alt, &c->v_alt, &c->stage_a, &c->stage_b, &c->stage_c, &c->stage_i,
+                    &c->runs, &c->cutneighsq, &c->atom_bin, &c->bin_atoms, &c->bincount, &c->bin_start, &c->cursor,
+                    &c->tile_sums, &c->numneigh, &c->neighbors, &c->lj_cut, &c->lj_s6, &c->lj_eps, &c->eam_rho_val,
+                    &c->eam_rho_der, &c->eam_z2_val, &c->eam_z2_der, &c->eam_frho_val, &c->eam_frho_der, &c->eam_cut,
+                    &c->rho, &c->fp, &c->border_tiles, &c->sendbuf, &c->recvbuf};
+  for (DevBuf* b : bufs) b->release();
+  for (int w = 0; w < MMD_MAX_SWAPS; w++) c->sw[w].list.release();
+#ifdef MMD_WITH_NCCL
+  if (c->nccl) ncclCommDestroy(c->nccl);
+#endif
+  cudaFree(c->d_scal); cudaFree(c->d_total); cudaFree(c->d_ev);
+  cudaFreeHost(c->h_scal); cudaFreeHost(c->h_total); cudaFreeHost(c->h_ev);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return MMD_OK;
+}
+
+int mmd_ctx_sync(mmd_ctx* c) {
+  CHECK_CTX(c);
+  CU(cudaStreamSynchronize(c->stream));
+  return MMD_OK;
+}
+void* mmd_ctx_stream(mmd_ctx* c) { return c ? (void*)c->stream : nullptr; }
+long long mmd_ctx_launches(mmd_ctx* c) { return c ? c->launches : 0; }
+
+// ---- Atom ------------------------------------------------------------------------------
+int mmd_atom_set_box(mmd_ctx* c, const double prd[3], const double lo[3], const double hi[3]) {
+  CHECK_CTX(c);
+  for (int d = 0; d < 3; d++) {
+    if (!(prd[d] > 0)) return set_err(MMD_ERR_ARG, "box length must be positive");
+    c->prd[d] = prd[d]; c->lo[d] = lo[d]; c->hi[d] = hi[d];
+  }
+  c->have_box = true;
+  return MMD_OK;
+}
+int mmd_atom_upload(mmd_ctx* c, const void* x, const void* v, const int* type, int nlocal, int pad) {
+  CHECK_CTX(c);
+  if (!x || !v || nlocal < 0 || (pad != 3 && pad != 4)) return set_err(MMD_ERR_ARG, "atom_upload: bad arguments");
+  return DISPATCH(c, Impl<double>::upload(c, x, v, type, nlocal, pad), Impl<float>::upload(c, x, v, type, nlocal, pad));
+}
+int mmd_atom_update(mmd_ctx* c, const void* x, const void* v, int first, int count, int pad) {
+  CHECK_CTX(c);
+  if (pad != 3 && pad != 4) return set_err(MMD_ERR_ARG, "pad must be 3 or 4");
+  return DISPATCH(c, Impl<double>::update(c, x, v, first, count, pad), Impl<float>::update(c, x, v, first, count, pad));
+}
+int mmd_atom_download(mmd_ctx* c, void* x, void* v, void* f, int* type, int first, int count, int pad) {
+  CHECK_CTX(c);
+  if (pad != 3 && pad != 4) return set_err(MMD_ERR_ARG, "pad must be 3 or 4");
+  return DISPATCH(c, Impl<double>::download(c, x, v, f, type, first, count, pad),
+                  Impl<float>::download(c, x, v, f, type, first, count, pad));
+}
+int mmd_atom_counts(mmd_ctx* c, int* nlocal, int* nghost, int* nmax) {
+  if (!c) return set_err(MMD_ERR_ARG, "null context");
+  if (nlocal) *nlocal = c->nlocal;
+  if (nghost) *nghost = c->nghost;
+  if (nmax) *nmax = c->cap;
+  return MMD_OK;
+}
+int mmd_atom_pbc(mmd_ctx* c) {
+  CHECK_CTX(c);
+  return DISPATCH(c, Impl<double>::pbc(c), Impl<float>::pbc(c));
+}
+int mmd_atom_sort(mmd_ctx* c) {
+  CHECK_CTX(c);
+  MM(DISPATCH(c, Impl<double>::sort(c), Impl<float>::sort(c)));
+  return DISPATCH(c, Impl<double>::read_status(c), Impl<float>::read_status(c));
+}
+
+// ---- Neighbor --------------------------------------------------------------------------
+int mmd_neigh_setup(mmd_ctx* c, const mmd_bin_geometry* g, const int* stencil, int nstencil, const void* cutneighsq) {
+  CHECK_CTX(c);
+  if (!g || !stencil || nstencil <= 0 || !cutneighsq) return set_err(MMD_ERR_ARG, "neigh_setup: bad arguments");
+  if (g->mbinx <= 0 || g->mbiny <= 0 || g->mbinz <= 0) return set_err(MMD_ERR_ARG, "neigh_setup: bad bin counts");
+  const long long mb = (long long)g->mbinx * g->mbiny * g->mbinz;
+  if (mb > 0x7fffffff - 2) return set_err(MMD_ERR_ARG, "neigh_setup: too many bins");
+  c->geo = *g;
+  c->mbins = (int)mb;
+  c->stencil.assign(stencil, stencil + nstencil);
+  // decompose the stencil into runs of consecutive bin offsets, preserving its order
+  std::vector<int2> runs;
+  for (int k = 0; k < nstencil; k++) {
+    if (!runs.empty() && runs.back().x + runs.back().y == stencil[k]) runs.back().y++;
+    else runs.push_back(make_int2(stencil[k], 1));
+  }
+  c->nruns = (int)runs.size();
+  MM(c->runs.reserve(runs.size() * sizeof(int2), c->stream));
+  CU(cudaMemcpy(c->runs.p, runs.data(), runs.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  const size_t nn = (size_t)c->ntypes * c->ntypes * c->prec;
+  MM(c->cutneighsq.reserve(nn, c->stream));
+  CU(cudaMemcpy(c->cutneighsq.p, cutneighsq, nn, cudaMemcpyHostToDevice));
+  MM(c->bincount.reserve((size_t)(mb + 1) * sizeof(int), c->stream));
+  MM(c->bin_start.reserve((size_t)(mb + 1) * sizeof(int), c->stream));
+  MM(c->cursor.reserve((size_t)(mb + 1) * sizeof(int), c->stream));
+  c->have_geo = true;
+  c->neigh_rows = -1;
+  return MMD_OK;
+}
+
+static int ref_atoms_per_bin(int current, int max_count) {  // ref/neighbor.cpp:257-261
+  int apb = current > 0 ? current : 8;
+  while (max_count > apb) apb *= 2;
+  return apb;
+}
+
+int mmd_neigh_binatoms(mmd_ctx* c, int count, int* atoms_per_bin, int* max_count) {
+  CHECK_CTX(c);
+  const int n = count < 0 ? c->nlocal + c->nghost : count;
+  if (n > c->nlocal + c->nghost) return set_err(MMD_ERR_ARG, "binatoms: count exceeds atoms");
+  MM(DISPATCH(c, Impl<double>::binatoms_async(c, n), Impl<float>::binatoms_async(c, n)));
+  MM(DISPATCH(c, Impl<double>::read_status(c), Impl<float>::read_status(c)));
+  if (max_count) *max_count = c->max_bin_seen;
+  if (atoms_per_bin) *atoms_per_bin = ref_atoms_per_bin(*atoms_per_bin, c->max_bin_seen);
+  return MMD_OK;
+}
+
+int mmd_neigh_build(mmd_ctx* c, int halfneigh, int ghost_newton, int* maxneighs, long long* total) {
+  CHECK_CTX(c);
+  if (!c->have_geo) return set_err(MMD_ERR_STATE, "neigh_build: mmd_neigh_setup missing");
+  return DISPATCH(c, Impl<double>::build(c, halfneigh, ghost_newton, maxneighs, total),
+                  Impl<float>::build(c, halfneigh, ghost_newton, maxneighs, total));
+}
+
+int mmd_neigh_download(mmd_ctx* c, int* numneigh, int* neighbors, int nrows, int maxneighs) {
+  CHECK_CTX(c);
+  if (nrows < 0 || nrows > c->neigh_rows) return set_err(MMD_ERR_ARG, "neigh_download: nrows exceeds built rows");
+  if (numneigh) CU(cudaMemcpyAsync(numneigh, c->numneigh.p, (size_t)nrows * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (neighbors) {
+    if (maxneighs < 1) return set_err(MMD_ERR_ARG, "neigh_download: maxneighs");
+    const int ncopy = std::min(maxneighs, c->maxneighs);
+    MM(c->stage_i.reserve((size_t)nrows * maxneighs * sizeof(int), c->stream));
+    CU(cudaMemsetAsync(c->stage_i.p, 0xff, (size_t)nrows * maxneighs * sizeof(int), c->stream));
+    const long long tot = (long long)nrows * ncopy;
+    LAUNCH(c, rows_restride_kernel, div_up(tot, TPB), TPB, c->neighbors.as<int>(), nrows, c->neigh_stride, maxneighs,
+           ncopy, c->stage_i.as<int>());
+    CU(cudaMemcpyAsync(neighbors, c->stage_i.p, (size_t)nrows * maxneighs * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return MMD_OK;
+}
+
+int mmd_neigh_upload(mmd_ctx* c, const int* numneigh, const int* neighbors, int nrows, int maxneighs) {
+  CHECK_CTX(c);
+  if (!numneigh || !neighbors || nrows != c->nlocal || maxneighs < 1) return set_err(MMD_ERR_ARG, "neigh_upload: bad arguments (nrows must equal nlocal)");
+  c->maxneighs = maxneighs;
+  c->neigh_stride = (maxneighs + 7) & ~7;
+  MM(c->numneigh.reserve((size_t)std::max(nrows, 1) * sizeof(int), c->stream));
+  MM(c->neighbors.reserve((size_t)std::max(nrows, 1) * c->neigh_stride * sizeof(int), c->stream));
+  MM(c->stage_i.reserve((size_t)nrows * maxneighs * sizeof(int), c->stream));
+  CU(cudaMemcpyAsync(c->numneigh.p, numneigh, (size_t)nrows * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->stage_i.p, neighbors, (size_t)nrows * maxneighs * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  const long long tot = (long long)nrows * maxneighs;
+  LAUNCH(c, rows_restride_kernel, div_up(tot, TPB), TPB, c->stage_i.as<int>(), nrows, maxneighs, c->neigh_stride, maxneighs,
+         c->neighbors.as<int>());
+  CU(cudaStreamSynchronize(c->stream));
+  c->neigh_rows = nrows;
+  return MMD_OK;
+}
+
+int mmd_neigh_bins_download(mmd_ctx* c, int* bincount, int* bins, int atoms_per_bin) {
+  CHECK_CTX(c);
+  if (!c->have_geo) return set_err(MMD_ERR_STATE, "bins_download: mmd_neigh_setup missing");
+  const int mb = c->mbins;
+  if (bincount) {
+    MM(c->stage_i.reserve((size_t)mb * sizeof(int), c->stream));
+    LAUNCH(c, bin_counts_from_start_kernel, div_up(mb, TPB), TPB, c->bin_start.as<int>(), mb, c->stage_i.as<int>());
+    CU(cudaMemcpyAsync(bincount, c->stage_i.p, (size_t)mb * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  if (bins) {
+    if (atoms_per_bin < 1) return set_err(MMD_ERR_ARG, "bins_download: atoms_per_bin");
+    MM(c->stage_i.reserve((size_t)mb * atoms_per_bin * sizeof(int), c->stream));
+    LAUNCH(c, bins_to_rows_kernel, div_up(mb, TPB), TPB, c->bin_start.as<int>(), c->bin_atoms.as<int>(), mb, atoms_per_bin,
+           c->stage_i.as<int>());
+    CU(cudaMemcpyAsync(bins, c->stage_i.p, (size_t)mb * atoms_per_bin * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return MMD_OK;
+}
+
+int mmd_neigh_atom_bins_download(mmd_ctx* c, int* bin_of_atom, int count) {
+  CHECK_CTX(c);
+  if (!bin_of_atom || count < 0 || count > c->binned_count) return set_err(MMD_ERR_ARG, "atom_bins_download: count exceeds last binning");
+  CU(cudaMemcpyAsync(bin_of_atom, c->atom_bin.p, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return MMD_OK;
+}
+
+// ---- Force -----------------------------------------------------------------------------
+int mmd_force_lj_setup(mmd_ctx* c, const void* cutforcesq, const void* sigma6, const void* epsilon) {
+  CHECK_CTX(c);
+  if (!cutforcesq || !sigma6 || !epsilon) return set_err(MMD_ERR_ARG, "force_lj_setup: null table");
+  const int nn = c->ntypes * c->ntypes;
+  const size_t nb = (size_t)nn * c->prec;
+  MM(c->lj_cut.reserve(nb, c->stream));
+  MM(c->lj_s6.reserve(nb, c->stream));
+  MM(c->lj_eps.reserve(nb, c->stream));
+  CU(cudaMemcpy(c->lj_cut.p, cutforcesq, nb, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c->lj_s6.p, sigma6, nb, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c->lj_eps.p, epsilon, nb, cudaMemcpyHostToDevice));
+  if (c->prec == 8) {
+    const double *a = (const double*)cutforcesq, *b = (const double*)sigma6, *e = (const double*)epsilon;
+    c->lj_uniform = all_equal(a, nn) && all_equal(b, nn) && all_equal(e, nn);
+    c->lj_cut0 = a[0]; c->lj_s60 = b[0]; c->lj_eps0 = e[0];
+  } else {
+    const float *a = (const float*)cutforcesq, *b = (const float*)sigma6, *e = (const float*)epsilon;
+    c->lj_uniform = all_equal(a, nn) && all_equal(b, nn) && all_equal(e, nn);
+    c->lj_cut0 = a[0]; c->lj_s60 = b[0]; c->lj_eps0 = e[0];
+  }
+  c->have_lj = true;
+  return MMD_OK;
+}
+
+static void store_real(mmd_ctx* c, void* dst, double v) {
+  if (!dst) return;
+  if (c->prec == 8) *(double*)dst = v;
+  else *(float*)dst = (float)v;
+}
+
+int mmd_force_lj_compute(mmd_ctx* c, int halfneigh, int ghost_newton, int evflag, void* eng_vdwl, void* virial) {
+  CHECK_CTX(c);
+  MM(DISPATCH(c, Impl<double>::lj_async(c, halfneigh, ghost_newton, evflag, true),
+              Impl<float>::lj_async(c, halfneigh, ghost_newton, evflag, true)));
+  if (evflag && (eng_vdwl || virial)) {
+    MM(Impl<double>::read_ev(c, 2));
+    store_real(c, eng_vdwl, c->h_ev[0]);
+    store_real(c, virial, c->h_ev[1]);
+  }
+  return MMD_OK;
+}
+
+int mmd_force_eam_setup(mmd_ctx* c, const void* rhor_spline, const void* z2r_spline, const void* frho_spline, int nr,
+                        int nrho, int nr_tot, int nrho_tot, double rdr, double rdrho, const void* cutforcesq) {
+  CHECK_CTX(c);
+  if (!rhor_spline || !z2r_spline || !frho_spline || !cutforcesq) return set_err(MMD_ERR_ARG, "force_eam_setup: null table");
+  if (nr < 2 || nrho < 2 || nr_tot < (nr + 1) * 7 || nrho_tot < (nrho + 1) * 7) return set_err(MMD_ERR_ARG, "force_eam_setup: table sizes");
+  return DISPATCH(c, Impl<double>::eam_setup(c, rhor_spline, z2r_spline, frho_spline, nr, nrho, nr_tot, nrho_tot, rdr, rdrho, cutforcesq),
+                  Impl<float>::eam_setup(c, rhor_spline, z2r_spline, frho_spline, nr, nrho, nr_tot, nrho_tot, rdr, rdrho, cutforcesq));
+}
+
+int mmd_force_eam_compute(mmd_ctx* c, int halfneigh, int evflag, void* eng_vdwl, void* virial) {
+  CHECK_CTX(c);
+  MM(DISPATCH(c, Impl<double>::eam_async(c, halfneigh, evflag), Impl<float>::eam_async(c, halfneigh, evflag)));
+  if (evflag && (eng_vdwl || virial)) {
+    MM(Impl<double>::read_ev(c, 4));
+    store_real(c, eng_vdwl, Impl<double>::eam_energy(c, halfneigh));
+    store_real(c, virial, c->h_ev[1]);
+  }
+  return MMD_OK;
+}
+
+// ---- Integrate / Thermo ----------------------------------------------------------------
+int mmd_integrate_initial(mmd_ctx* c, double dt, double dtforce) {
+  CHECK_CTX(c);
+  return DISPATCH(c, Impl<double>::initial(c, dt, dtforce, false), Impl<float>::initial(c, dt, dtforce, false));
+}
+int mmd_integrate_final(mmd_ctx* c, double dtforce) {
+  CHECK_CTX(c);
+  return DISPATCH(c, Impl<double>::final_(c, dtforce, false, 1.0), Impl<float>::final_(c, dtforce, false, 1.0));
+}
+int mmd_thermo_sum_mv2(mmd_ctx* c, double mass, double* sum_mv2) {
+  CHECK_CTX(c);
+  if (!sum_mv2) return set_err(MMD_ERR_ARG, "sum_mv2: null output");
+  return DISPATCH(c, Impl<double>::sum_mv2(c, mass, sum_mv2), Impl<float>::sum_mv2(c, mass, sum_mv2));
+}
+
+// ---- Comm ------------------------------------------------------------------------------
+int mmd_comm_setup(mmd_ctx* c, const mmd_swap_table* t) {
+  CHECK_CTX(c);
+  if (!t || t->nswap < 0 || t->nswap > MMD_MAX_SWAPS || (t->nswap % 2)) return set_err(MMD_ERR_ARG, "comm_setup: bad swap table");
+  if (t->nswap != 2 * (t->need[0] + t->need[1] + t->need[2])) return set_err(MMD_ERR_ARG, "comm_setup: nswap != 2*sum(need)");
+  c->swaps = *t;
+  for (int w = 0; w < MMD_MAX_SWAPS; w++) c->sw[w].sendnum = c->sw[w].recvnum = c->sw[w].firstrecv = 0;
+  c->have_comm = true;
+  return MMD_OK;
+}
+
+int mmd_comm_nccl_unique_id(void* id128) {
+#ifdef MMD_WITH_NCCL
+  if (!id128) return set_err(MMD_ERR_ARG, "null id");
+  ncclUniqueId id;
+  NC(ncclGetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(id128, &id, 128);
+  return MMD_OK;
+#else
+  (void)id128;
+  return set_err(MMD_ERR_STATE, "library built without NCCL");
+#endif
+}
+int mmd_comm_nccl_init(mmd_ctx* c, const void* id128, int rank, int nranks) {
+  CHECK_CTX(c);
+#ifdef MMD_WITH_NCCL
+  if (!id128 || rank < 0 || rank >= nranks) return set_err(MMD_ERR_ARG, "nccl_init: bad arguments");
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  NC(ncclCommInitRank(&c->nccl, nranks, id, rank));
+  c->rank = rank;
+  c->nranks = nranks;
+  return MMD_OK;
+#else
+  (void)id128; (void)rank; (void)nranks;
+  return set_err(MMD_ERR_STATE, "library built without NCCL");
+#endif
+}
+
+int mmd_comm_exchange(mmd_ctx* c) {
+  CHECK_CTX(c);
+  if (!c->have_comm) return set_err(MMD_ERR_STATE, "exchange: mmd_comm_setup missing");
+  return DISPATCH(c, Impl<double>::exchange(c), Impl<float>::exchange(c));
+}
+int mmd_comm_borders(mmd_ctx* c) {
+  CHECK_CTX(c);
+  return DISPATCH(c, Impl<double>::borders(c), Impl<float>::borders(c));
+}
+int mmd_comm_communicate(mmd_ctx* c) {
+  CHECK_CTX(c);
+  return DISPATCH(c, Impl<double>::communicate(c, false), Impl<float>::communicate(c, false));
+}
+int mmd_comm_reverse_communicate(mmd_ctx* c) {
+  CHECK_CTX(c);
+  return DISPATCH(c, Impl<double>::reverse(c), Impl<float>::reverse(c));
+}
+int mmd_comm_swap_counts(mmd_ctx* c, int* sendnum, int* recvnum, int* firstrecv) {
+  if (!c) return set_err(MMD_ERR_ARG, "null context");
+  for (int w = 0; w < c->swaps.nswap; w++) {
+    if (sendnum) sendnum[w] = c->sw[w].sendnum;
+    if (recvnum) recvnum[w] = c->sw[w].recvnum;
+    if (firstrecv) firstrecv[w] = c->sw[w].firstrecv;
+  }
+  return MMD_OK;
+}
+int mmd_comm_sendlist_download(mmd_ctx* c, int iswap, int* list, int count) {
+  CHECK_CTX(c);
+  if (iswap < 0 || iswap >= c->swaps.nswap || !list || count < 0 || count > c->sw[iswap].sendnum)
+    return set_err(MMD_ERR_ARG, "sendlist_download: bad arguments");
+  CU(cudaMemcpyAsync(list, c->sw[iswap].list.p, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return MMD_OK;
+}
+int mmd_comm_allreduce(mmd_ctx* c, double* values, int n, int op) {
+  CHECK_CTX(c);
+  if (!values || n < 0 || n > 4) return set_err(MMD_ERR_ARG, "allreduce: n must be 0..4");
+  if (c->nranks <= 1) return MMD_OK;
+#ifdef MMD_WITH_NCCL
+  double* d = c->d_ev;  // reuse the scalar block
+  CU(cudaMemcpyAsync(d, values, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NC(ncclAllReduce(d, d, n, ncclDouble, op == 1 ? ncclMax : ncclSum, c->nccl, c->stream));
+  CU(cudaMemcpyAsync(values, d, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return MMD_OK;
+#else
+  return set_err(MMD_ERR_STATE, "library built without NCCL");
+#endif
+}
+
+// ---- time loop ---------------------------------------------------------------------------
+int mmd_run(mmd_ctx* c, const mmd_run_params* p, mmd_thermo_sample* samples, int max_samples, int* nsamples,
+            float* elapsed_ms) {
+  CHECK_CTX(c);
+  if (!p || p->ntimes < 0 || p->neigh_every < 1) return set_err(MMD_ERR_ARG, "run: bad parameters");
+  return DISPATCH(c, Impl<double>::run(c, p, samples, max_samples, nsamples, elapsed_ms),
+                  Impl<float>::run(c, p, samples, max_samples, nsamples, elapsed_ms));
+}
+
+// ---- introspection -------------------------------------------------------------------------
+int mmd_query_int(mmd_ctx* c, const char* key, long long* value) {
+  if (!c || !key || !value) return set_err(MMD_ERR_ARG, "query: null argument");
+  std::string k(key);
+  if (k == "nlocal") *value = c->nlocal;
+  else if (k == "nghost") *value = c->nghost;
+  else if (k == "nmax") *value = c->cap;
+  else if (k == "maxneighs") *value = c->maxneighs;
+  else if (k == "neigh_stride") *value = c->neigh_stride;
+  else if (k == "mbins") *value = c->mbins;
+  else if (k == "nstencil") *value = (long long)c->stencil.size();
+  else if (k == "nruns") *value = c->nruns;
+  else if (k == "total_neigh") *value = c->total_neigh;
+  else if (k == "neigh_builds") *value = c->neigh_builds;
+  else if (k == "neigh_resizes") *value = c->neigh_resizes;
+  else if (k == "max_bin_count") *value = c->max_bin_seen;
+  else if (k == "atoms_per_bin") *value = ref_atoms_per_bin(8, c->max_bin_seen);
+  else if (k == "nswap") *value = c->swaps.nswap;
+  else if (k == "precision") *value = c->prec;
+  else if (k == "ntypes") *value = c->ntypes;
+  else if (k == "lj_uniform") *value = c->lj_uniform;
+  else if (k == "eam_uniform") *value = c->eam_uniform;
+  else if (k == "lj_threads_per_atom") *value = c->lj_tpa;
+  else if (k == "eam_threads_per_atom") *value = c->eam_tpa;
+  else if (k == "launches") *value = c->launches;
+  else return set_err(MMD_ERR_ARG, "query: unknown key '%s'", key);
+  return MMD_OK;
+}
+
+int mmd_set_option(mmd_ctx* c, const char* key, long long value) {
+  if (!c || !key) return set_err(MMD_ERR_ARG, "set_option: null argument");
+  std::string k(key);
+  auto pow2 = [](long long v) { return v >= 1 && v <= 32 && (v & (v - 1)) == 0; };
+  if (k == "lj_threads_per_atom") {
+    if (!pow2(value)) return set_err(MMD_ERR_ARG, "lj_threads_per_atom must be 1,2,4,8,16 or 32");
+    c->lj_tpa = (int)value;
+  } else if (k == "eam_threads_per_atom") {
+    if (!pow2(value)) return set_err(MMD_ERR_ARG, "eam_threads_per_atom must be 1,2,4,8,16 or 32");
+    c->eam_tpa = (int)value;
+  } else if (k == "force_nonuniform") {  // testing: exercise the per-type table path
+    if (value) { c->lj_uniform = false; c->eam_uniform = false; }
+  } else {
+    return set_err(MMD_ERR_ARG, "set_option: unknown key '%s'", key);
+  }
+  return MMD_OK;
+}
+
+}  // extern "C"

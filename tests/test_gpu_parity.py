@@ -1,0 +1,306 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle on the same
+seeded inputs.  Integer / index work must be bit-exact; floating point within the stated
+tolerances (FP64: 1e-11 relative per kernel, 1e-9 on T/U/P over 100 steps; the reference's
+own acceptance is 1e-5).
+"""
+import numpy as np
+import pytest
+
+from helpers import context_from_oracle, rel, run_params, thermo_from_samples
+from oracle.oracle import Config, Oracle
+
+pytestmark = pytest.mark.gpu
+
+F64_KERNEL_RTOL = 1e-11
+F32_KERNEL_RTOL = 2e-4
+
+
+def ktol(prec):
+    return F64_KERNEL_RTOL if prec == "f64" else F32_KERNEL_RTOL
+
+
+def maxabs(a):
+    return float(np.max(np.abs(a))) if np.size(a) else 0.0
+
+
+def assert_close(a, b, rtol, what=""):
+    scale = max(maxabs(b), 1e-300)
+    err = maxabs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)) / scale
+    assert err <= rtol, f"{what}: max err {err:.3e} > {rtol:.1e} (scale {scale:.3e})"
+
+
+def melted(cfg_kwargs, steps, prec="f64"):
+    """Oracle advanced to a re-neighboring step, so x / ghosts / lists are mutually consistent."""
+    cfg = Config(**cfg_kwargs)
+    o = Oracle(cfg, prec)
+    if steps:
+        assert steps % cfg.resolved().neigh_every == 0
+        o.run(steps)
+    return o
+
+
+CASES = [
+    dict(nx=8, ny=8, nz=8, halfneigh=1, ghost_newton=1),
+    dict(nx=8, ny=8, nz=8, halfneigh=1, ghost_newton=0),
+    dict(nx=8, ny=8, nz=8, halfneigh=0, ghost_newton=0),
+    dict(nx=6, ny=8, nz=10, halfneigh=1, ghost_newton=1, sort=0),
+    dict(nx=3, ny=3, nz=3, halfneigh=0, ghost_newton=1),
+]
+
+
+# ------------------------------------------------------------------------------------------
+# binning / borders / neighbor build / sort : bit-exact
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("steps", [0, 40])
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_borders_bins_and_lists_are_bit_exact(case, steps, prec):
+    o = melted(CASES[case], steps, prec)
+    c = context_from_oracle(o)
+    c.exchange()
+    c.borders()
+    # ghosts: counts, send lists, positions (+- prd shifts) and types
+    assert c.counts()[:2] == (o.nlocal, o.nghost)
+    sn, rn, fr = c.swap_counts()
+    ns = o.geti("nswap")
+    assert list(sn) == list(o.ivec("sendnum", ns)) and list(fr) == list(o.ivec("firstrecv", ns))
+    for w in range(ns):
+        assert np.array_equal(c.sendlist(w), o.sendlist(w)), f"sendlist {w}"
+    d = c.download("xt")
+    assert np.array_equal(d["x"], o.x()), "ghost positions differ"
+    assert np.array_equal(d["type"], o.type())
+    # bins
+    apb, mx = c.binatoms(-1, 8)
+    o.call("binatoms", -1)
+    assert apb == o.geti("atoms_per_bin")
+    cnt, rows = c.bins_download(apb)
+    assert np.array_equal(cnt, o.bincount())
+    ob = o.bins()
+    for b in np.nonzero(cnt)[0]:
+        assert np.array_equal(rows[b, :cnt[b]], ob[b, :cnt[b]])
+    # neighbor lists
+    half, gn = o.geti("halfneigh"), o.geti("ghost_newton")
+    mxn, total = c.build(half, gn, 100)
+    num, nb = c.neigh_download()
+    onum, onb = o.numneigh(), o.neighbors()
+    assert mxn == o.geti("maxneighs")
+    assert total == int(onum.sum())
+    assert np.array_equal(num, onum)
+    for i in range(o.nlocal):
+        assert np.array_equal(nb[i, :num[i]], onb[i, :num[i]]), f"row {i}"
+
+
+def test_neighbor_resize_protocol_matches_reference():
+    o = Oracle(Config(nx=6, ny=6, nz=6, halfneigh=0), "f64")
+    c = context_from_oracle(o)
+    c.exchange()
+    c.borders()
+    o.seti("maxneighs", 20)
+    o.call("neighbor_build")
+    mxn, total = c.build(0, 1, 20)
+    assert mxn == o.geti("maxneighs") and mxn > 20
+    assert c.query("neigh_resizes") >= 1
+    num, nb = c.neigh_download()
+    assert np.array_equal(num, o.numneigh())
+    onb = o.neighbors()
+    for i in range(0, o.nlocal, 7):
+        assert np.array_equal(nb[i, :num[i]], onb[i, :num[i]])
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_sort_permutation_is_the_reference_order(prec):
+    o = melted(dict(nx=8, ny=8, nz=8, sort=0), 40, prec)   # never sorted so far
+    c = context_from_oracle(o)
+    c.sort()
+    o.call("sort")
+    d = c.download("xvt", count=o.nlocal)
+    assert np.array_equal(d["x"], o.x(o.nlocal))
+    assert np.array_equal(d["v"], o.v())
+    assert np.array_equal(d["type"], o.type(o.nlocal))
+
+
+def test_coord2bin_edge_cases_bit_exact():
+    """Atoms exactly on bin / box boundaries and ghosts outside [0,prd)."""
+    o = Oracle(Config(nx=4, ny=4, nz=4), "f64")
+    prd = o.getr("box.xprd")
+    bs = 1.0 / o.getr("bininvx")
+    rng = np.random.default_rng(7)
+    n = 4096
+    x = rng.uniform(-2.7, prd + 2.7, size=(n, 3))
+    edges = np.array([0.0, prd, bs, 2 * bs, prd - bs, np.nextafter(prd, 0), np.nextafter(0.0, -1), -bs, prd + bs,
+                      np.nextafter(bs, 0), np.nextafter(bs, 10)])
+    x[:edges.size * 3] = np.repeat(edges, 3)[:, None]
+    x[:edges.size, 1] = rng.uniform(0, prd, edges.size)
+    c = context_from_oracle(o, upload_atoms=False)
+    c.upload(x, np.zeros_like(x), np.zeros(n, dtype=np.int32))
+    c.binatoms(n, 8)
+    got = c.atom_bins(n)
+    lib = o.lib
+    import ctypes as C
+    lib.orc_coord2bin.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+    want = np.array([lib.orc_coord2bin(o.h, *map(float, p)) for p in x], dtype=np.int32)
+    assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------------------------------
+# forces
+# ------------------------------------------------------------------------------------------
+def setup_lists(o):
+    c = context_from_oracle(o)
+    c.exchange()
+    c.borders()
+    c.build(o.geti("halfneigh"), o.geti("ghost_newton"), 100)
+    return c
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("tpa", [1, 4, 8, 32])
+@pytest.mark.parametrize("half,gn", [(1, 1), (1, 0), (0, 0)])
+def test_lj_force_energy_virial(half, gn, tpa, prec):
+    o = melted(dict(nx=8, ny=8, nz=8, halfneigh=half, ghost_newton=gn), 40, prec)
+    c = setup_lists(o)
+    c.set_option("lj_threads_per_atom", tpa)
+    o.seti("evflag", 1)
+    o.call("force_compute")
+    eng, vir = c.lj_compute(half, gn, 1)
+    n = o.nall if half else o.nlocal
+    f = c.download("f", count=n)["f"]
+    assert_close(f, o.f(n), ktol(prec), "f")
+    # the FP32 reference accumulates energy in one float; the device reduces in FP64
+    etol = 1e-11 if prec == "f64" else 2e-3
+    assert abs(eng - o.getr("eng_vdwl")) <= etol * abs(o.getr("eng_vdwl"))
+    assert abs(vir - o.getr("virial")) <= etol * max(abs(o.getr("virial")), abs(o.getr("eng_vdwl")))
+    # evflag=0 path gives the same forces
+    c.lj_compute(half, gn, 0)
+    f0 = c.download("f", count=n)["f"]
+    assert_close(f0, f, 1e-13 if prec == "f64" else 1e-5, "f(ev=0) vs f(ev=1)")
+
+
+def test_lj_per_type_tables_path():
+    """Distinct epsilon/sigma per type pair exercises the non-uniform table kernels."""
+    o = melted(dict(nx=6, ny=6, nz=6, halfneigh=0, ghost_newton=0, ntypes=3), 20, "f64")
+    nn = 9
+    rng = np.random.default_rng(3)
+    eps = o.rvec("epsilon", nn); s6 = o.rvec("sigma6", nn); cut = o.rvec("cutforcesq", nn)
+    sym = lambda a: (a + a.T) / 2
+    eps[:] = sym(rng.uniform(0.8, 1.2, (3, 3))).ravel()
+    s6[:] = sym(rng.uniform(0.9, 1.1, (3, 3))).ravel()
+    cut[:] = sym(rng.uniform(5.0, 6.25, (3, 3))).ravel()
+    c = setup_lists(o)
+    assert c.query("lj_uniform") == 0
+    o.seti("evflag", 1)
+    o.call("force_compute")
+    eng, vir = c.lj_compute(0, 0, 1)
+    assert_close(c.download("f", count=o.nlocal)["f"], o.f(o.nlocal), 1e-11, "f")
+    assert abs(eng - o.getr("eng_vdwl")) <= 1e-11 * abs(o.getr("eng_vdwl"))
+    assert abs(vir - o.getr("virial")) <= 1e-10 * abs(o.getr("eng_vdwl"))
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("half", [1, 0])
+@pytest.mark.parametrize("uniform", [1, 0])
+def test_eam_force_energy_virial(half, uniform, prec):
+    o = melted(dict(nx=6, ny=6, nz=6, force="eam", halfneigh=half, ghost_newton=0), 20, prec)
+    c = setup_lists(o)
+    if not uniform:
+        c.set_option("force_nonuniform", 1)
+    o.seti("evflag", 1)
+    o.call("force_compute")
+    eng, vir = c.eam_compute(half, 1)
+    n = o.nall if half else o.nlocal
+    f = c.download("f", count=n)["f"]
+    assert_close(f, o.f(n), 1e-10 if prec == "f64" else 5e-4, "f")
+    etol = 1e-11 if prec == "f64" else 1e-4
+    assert abs(eng - o.getr("eng_vdwl")) <= etol * abs(o.getr("eng_vdwl"))
+    assert abs(vir - o.getr("virial")) <= max(etol, 1e-10) * max(abs(o.getr("virial")), 1.0) * 10
+
+
+# ------------------------------------------------------------------------------------------
+# integrate / halo / thermo
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_integrate_pbc_halo_and_thermo_kernels(prec):
+    o = melted(dict(nx=8, ny=8, nz=8), 40, prec)
+    c = setup_lists(o)
+    nl, na = o.nlocal, o.nall
+    tol = 1e-14 if prec == "f64" else 1e-6
+    # forces first (both sides), then reverse halo
+    o.seti("evflag", 0)
+    o.call("force_compute")
+    c.lj_compute(1, 1, 0)
+    o.call("reverse_communicate")
+    c.reverse_communicate()
+    assert_close(c.download("f", count=nl)["f"], o.f(nl), ktol(prec), "f after reverse")
+    # make device f identical to the oracle's so the integrator is tested in isolation
+    dt, dtf = o.getr("dt"), o.getr("dtforce")
+    # (velocity-Verlet halves: FMA contraction on the device => 1 ulp)
+    o.call("final_integrate")
+    c.final_integrate(dtf)
+    assert_close(c.download("v")["v"], o.v(), max(tol, ktol(prec)), "v final")
+    mv2 = c.sum_mv2(o.getr("mass"))
+    want = float(np.sum(o.v().astype(np.float64) ** 2) * o.getr("mass"))
+    assert abs(mv2 - want) <= 1e-6 * want
+    o.call("initial_integrate")
+    c.initial_integrate(dt, dtf)
+    d = c.download("xv", count=nl)
+    assert_close(d["x"], o.x(nl), max(tol, ktol(prec)), "x initial")
+    assert_close(d["v"], o.v(), max(tol, ktol(prec)), "v initial")
+    # forward halo: ghosts follow their owners exactly (same inputs => compare device with itself)
+    o.call("communicate")
+    c.communicate()
+    xs = c.download("x")["x"]
+    prd = np.array([o.getr("box.xprd"), o.getr("box.yprd"), o.getr("box.zprd")])
+    ns = o.geti("nswap")
+    sn, fr = o.ivec("sendnum", ns), o.ivec("firstrecv", ns)
+    flags = np.stack([o.ivec("pbc_flagx", ns), o.ivec("pbc_flagy", ns), o.ivec("pbc_flagz", ns)], axis=1)
+    ref = xs.copy()
+    for w in range(ns):
+        ref[fr[w]:fr[w] + sn[w]] = ref[o.sendlist(w)] + (flags[w] * prd).astype(xs.dtype)
+    assert np.array_equal(xs, ref), "forward halo is not an exact copy+shift"
+    assert_close(xs, o.x(), max(tol, ktol(prec)), "x after halo")
+    # pbc wrap: push some atoms out of the box and wrap on both sides
+    x = o.x(nl).copy()
+    x[::5] += prd.astype(x.dtype)
+    x[1::5] -= prd.astype(x.dtype)
+    o.x(nl)[:] = x
+    c.update(x=x)
+    o.call("pbc")
+    c.pbc()
+    assert np.array_equal(c.download("x", count=nl)["x"], o.x(nl))
+
+
+# ------------------------------------------------------------------------------------------
+# whole time loop
+# ------------------------------------------------------------------------------------------
+RUN_CASES = [
+    ("lj", 1, 1, "f64", 1e-9), ("lj", 1, 0, "f64", 1e-9), ("lj", 0, 0, "f64", 1e-9),
+    ("eam", 1, 0, "f64", 1e-9), ("eam", 0, 0, "f64", 1e-9),
+    ("lj", 0, 0, "f32", 1e-4), ("lj", 1, 1, "f32", 1e-4), ("eam", 0, 0, "f32", 1e-4),
+]
+
+
+@pytest.mark.parametrize("force,half,gn,prec,tol", RUN_CASES)
+def test_time_loop_matches_oracle(force, half, gn, prec, tol):
+    cfg = Config(nx=8, ny=8, nz=8, ntimes=100, force=force, halfneigh=half, ghost_newton=gn, thermo_nstat=10)
+    o64 = Oracle(cfg, "f64")          # FP32 runs are judged against the FP64 oracle
+    o = Oracle(cfg, prec)
+    c = context_from_oracle(o)
+    c.exchange()
+    c.borders()
+    c.build(o.geti("halfneigh"), o.geti("ghost_newton"), 100)
+    samples, ms = c.run(run_params(o, 100))
+    got = thermo_from_samples(o, samples)
+    o64.run(100)
+    st, T, U, P = o64.thermo_log()
+    assert [g[0] for g in got] == list(st[1:])
+    pscale = max(1.0, float(np.max(np.abs(P))))
+    for (step, t, e, p), tw, ew, pw in zip(got, T[1:], U[1:], P[1:]):
+        assert abs(t - tw) <= tol * abs(tw), (step, t, tw)
+        assert abs(e - ew) <= tol * abs(ew), (step, e, ew)
+        assert abs(p - pw) <= 10 * tol * pscale, (step, p, pw)
+    # integer pins at the end of the run
+    o.run(100)
+    assert c.counts()[:2] == (o.nlocal, o.nghost) or prec == "f32"
+    if prec == "f64":
+        assert c.query("total_neigh") == int(o.numneigh().sum())
+        assert c.query("maxneighs") == o.geti("maxneighs")
