@@ -210,7 +210,9 @@ def test_eam_force_energy_virial(half, uniform, prec):
     n = o.nall if half else o.nlocal
     f = c.download("f", count=n)["f"]
     assert_close(f, o.f(n), 1e-10 if prec == "f64" else 5e-4, "f")
-    etol = 1e-11 if prec == "f64" else 1e-4
+    # FP32: the reference (and so the oracle) accumulates energy/virial in ONE float over ~1e5 pairs
+    # (ref/force_eam.cpp:96,259); the device reduces in FP64 and is closer to the FP64 truth.
+    etol = 1e-11 if prec == "f64" else 2e-3
     assert abs(eng - o.getr("eng_vdwl")) <= etol * abs(o.getr("eng_vdwl"))
     assert abs(vir - o.getr("virial")) <= max(etol, 1e-10) * max(abs(o.getr("virial")), 1.0) * 10
 

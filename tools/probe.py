@@ -34,6 +34,33 @@ def timeit(ctx, fn, reps=5, warm=1):
     return float(np.median(ts))
 
 
+def profile_mode(a):
+    """One launch of each interesting kernel variant (run under `ncu -k regex:...`)."""
+    from helpers import geometry_of
+    gn = 1 if a.force == "lj" else 0
+    cfg = Config(nx=a.s, ny=a.s, nz=a.s, force=a.force, halfneigh=1, ghost_newton=gn)
+    o = Oracle(cfg, a.prec)
+    o.run(20)                      # a melted, re-neighbored state (sorted atoms), not the perfect lattice
+    c = context_from_oracle(o)
+    c.exchange(); c.borders()
+    key = "lj_threads_per_atom" if a.force == "lj" else "eam_threads_per_atom"
+    for half, g, tpas in ((1, gn, (2, 4, 8)), (0, 0, (2, 4, 8))):
+        o.seti("halfneigh", half); o.seti("ghost_newton", g); o.call("neighbor_setup")
+        c.neigh_setup(geometry_of(o), o.stencil(), o.rvec("cutneighsq", cfg.ntypes ** 2))
+        c.build(half, g, 100)
+        for tpa in tpas:
+            c.set_option(key, tpa)
+            for ev in (0, 1):
+                if a.force == "lj":
+                    c.lib.mmd_force_lj_compute(c.h, half, g, ev, None, None)
+                else:
+                    c.lib.mmd_force_eam_compute(c.h, half, ev, None, None)
+        c.sync()
+    c.initial_integrate(0.0, 0.0); c.final_integrate(0.0); c.communicate(); c.reverse_communicate()
+    c.sort(); c.borders(); c.sync()
+    print("profile mode done", c.launches)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("-s", type=int, default=80)
@@ -41,7 +68,10 @@ def main():
     ap.add_argument("--prec", default="f64")
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--out", default="gpurun_out/probe.json")
+    ap.add_argument("--profile", action="store_true", help="few launches only: meant to run under ncu")
     a = ap.parse_args()
+    if a.profile:
+        return profile_mode(a)
     res = {"size": a.s, "force": a.force, "prec": a.prec}
     gn = 1 if a.force == "lj" else 0
     cfg = Config(nx=a.s, ny=a.s, nz=a.s, force=a.force, halfneigh=1, ghost_newton=gn)
