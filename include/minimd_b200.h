@@ -160,7 +160,7 @@ int mmd_comm_swap_counts(mmd_ctx* ctx, int* sendnum, int* recvnum, int* firstrec
 /* Comm::sendlist[iswap] (int[sendnum[iswap]]). */
 int mmd_comm_sendlist_download(mmd_ctx* ctx, int iswap, int* list, int count);
 /* sum / max over ranks of n doubles (Thermo's MPI_Allreduce, ref/thermo.cpp:131,168,188);
- * identity on one rank. op: 0 sum, 1 max. */
+ * identity on one rank. op: 0 sum, 1 max; n <= 16. */
 int mmd_comm_allreduce(mmd_ctx* ctx, double* values, int n, int op);
 
 /* ---- fused time loop (Integrate::run, ref/integrate.cpp:70-207) ---------------------- */
@@ -187,6 +187,14 @@ typedef struct {
  * elapsed_ms (may be NULL): CUDA-event time of the loop on the context's stream. */
 int mmd_run(mmd_ctx* ctx, const mmd_run_params* params, mmd_thermo_sample* samples, int max_samples,
             int* nsamples, float* elapsed_ms);
+
+/* Device-time split of mmd_run, the analogue of the reference's Timer buckets (ref/timer.h:35-40:
+ * TIME_COMM / TIME_FORCE / TIME_NEIGH; "integrate" is what the reference reports as t_other).
+ * Enabled with mmd_set_option(ctx, "phase_timing", 1); measured with CUDA events on the context's
+ * stream.  ms[MMD_NPHASE] / calls[MMD_NPHASE] accumulate over mmd_run calls until reset != 0. */
+enum { MMD_PHASE_INTEGRATE = 0, MMD_PHASE_COMM = 1, MMD_PHASE_NEIGH = 2, MMD_PHASE_FORCE = 3, MMD_PHASE_OTHER = 4,
+       MMD_NPHASE = 5 };
+int mmd_run_phase_times(mmd_ctx* ctx, double* ms, long long* calls, int reset);
 
 /* ---- introspection ------------------------------------------------------------------- */
 /* Named integer/real queries ("nlocal", "nghost", "maxneighs", "mbins", "total_neigh",

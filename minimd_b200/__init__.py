@@ -6,5 +6,6 @@ This Python package only binds the C ABI for tests and bench.py; it contains no 
 """
 from ._lib import MmdError, load  # noqa: F401
 from .api import Context, nccl_unique_id  # noqa: F401
+from .host import HostError, Simulation, input_file, load_host  # noqa: F401
 
-__all__ = ["Context", "MmdError", "load", "nccl_unique_id"]
+__all__ = ["Context", "MmdError", "load", "nccl_unique_id", "Simulation", "HostError", "input_file", "load_host"]

@@ -97,6 +97,7 @@ SIGNATURES = {
     "mmd_comm_sendlist_download": (_I, [_P, _I, _P, _I]),
     "mmd_comm_allreduce": (_I, [_P, _DP, _I, _I]),
     "mmd_run": (_I, [_P, C.POINTER(RunParams), C.POINTER(ThermoSample), _I, _IP, C.POINTER(C.c_float)]),
+    "mmd_run_phase_times": (_I, [_P, _DP, _LLP, _I]),
     "mmd_query_int": (_I, [_P, C.c_char_p, _LLP]),
     "mmd_set_option": (_I, [_P, C.c_char_p, C.c_longlong]),
 }

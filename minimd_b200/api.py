@@ -29,7 +29,8 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.mmd_ctx_destroy(self.h)
+            if not getattr(self, "_borrowed", False):
+                self.lib.mmd_ctx_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -242,6 +243,15 @@ class Context:
                                C.byref(ms) if timed else None))
         out = [(s.step, s.sum_mv2, s.eng_vdwl, s.virial) for s in samples[:min(ns.value, max_samples)]]
         return out, (ms.value if timed else None)
+
+
+    def phase_times(self, reset: bool = False):
+        """{phase: (ms, intervals)} accumulated by run() while option phase_timing is on."""
+        ms = (C.c_double * 5)()
+        calls = (C.c_longlong * 5)()
+        check(self.lib.mmd_run_phase_times(self.h, ms, calls, int(reset)))
+        names = ("integrate", "comm", "neigh", "force", "other")
+        return {n: (ms[i], calls[i]) for i, n in enumerate(names)}
 
 
 def nccl_unique_id() -> bytes:

@@ -81,7 +81,7 @@ def build_host(force: bool = False) -> list[str]:
     for prec, tag in ((2, "f64"), (1, "f32")):
         so = os.path.join(LIB, f"libminimd_host_{tag}.so")
         exe = os.path.join(BIN, f"miniMD_b200_{tag}")
-        common = [CXX, "-O2", "-std=c++17", "-fPIC", f"-DPRECISION={prec}", f"-I{INC}", f"-I{hostdir}", "-Wall",
+        common = [CXX, "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", f"-DPRECISION={prec}", f"-I{INC}", f"-I{hostdir}", "-Wall",
                   "-Wno-unused-result"]
         link = [f"-L{LIB}", "-lminimd_b200", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/../lib"]
         if force or _newer(so, lib_srcs + hdrs):

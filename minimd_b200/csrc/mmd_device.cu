@@ -172,7 +172,45 @@ struct mmd_ctx {
   double* h_ev = nullptr;
 
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  // per-phase device timing of mmd_run (option "phase_timing"): marks[k] closes an interval of phase
+  // mark_phase[k]; intervals are summed after the loop's final synchronisation.
+  bool phase_timing = false;
+  std::vector<cudaEvent_t> marks;
+  std::vector<int> mark_phase;
+  int nmarks = 0;
+  double phase_ms[MMD_NPHASE] = {0, 0, 0, 0, 0};
+  long long phase_calls[MMD_NPHASE] = {0, 0, 0, 0, 0};
 };
+
+// close the interval since the previous mark and attribute it to `phase` (-1: just open an interval)
+static int phase_mark(mmd_ctx* c, int phase) {
+  if (!c->phase_timing) return MMD_OK;
+  if (c->nmarks == (int)c->marks.size()) {
+    cudaEvent_t e;
+    CU(cudaEventCreate(&e));
+    c->marks.push_back(e);
+    c->mark_phase.push_back(-1);
+  }
+  CU(cudaEventRecord(c->marks[c->nmarks], c->stream));
+  c->mark_phase[c->nmarks] = phase;
+  c->nmarks++;
+  return MMD_OK;
+}
+static int phase_collect(mmd_ctx* c) {
+  if (!c->phase_timing || c->nmarks == 0) return MMD_OK;
+  CU(cudaEventSynchronize(c->marks[c->nmarks - 1]));
+  for (int k = 1; k < c->nmarks; k++) {
+    const int ph = c->mark_phase[k];
+    if (ph < 0) continue;
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, c->marks[k - 1], c->marks[k]));
+    c->phase_ms[ph] += ms;
+    c->phase_calls[ph]++;
+  }
+  c->nmarks = 0;
+  return MMD_OK;
+}
 
 static const int TPB = 256;
 static int launch_fail(int line, cudaError_t e) {
@@ -806,10 +844,13 @@ template <class T> struct Impl {
     while (p->sort_every > 0 && next_sort <= p->first_step) next_sort += p->sort_every;
     const bool reverse_needed = p->halfneigh && p->ghost_newton;
     if (elapsed_ms) CU(cudaEventRecord(c->ev0, c->stream));
+    MM(phase_mark(c, -1));
     for (int n = p->first_step; n < p->first_step + p->ntimes; n++) {
       MM(initial(c, p->dt, p->dtforce, false));
+      MM(phase_mark(c, MMD_PHASE_INTEGRATE));
       if ((n + 1) % p->neigh_every) {
         MM(communicate(c, false));
+        MM(phase_mark(c, MMD_PHASE_COMM));
       } else {
         MM(exchange(c));
         if (n + 1 >= next_sort) {
@@ -817,14 +858,21 @@ template <class T> struct Impl {
           next_sort += p->sort_every;
         }
         MM(borders(c));
+        MM(phase_mark(c, MMD_PHASE_COMM));
         int mx = c->maxneighs;
         MM(build(c, p->halfneigh, p->ghost_newton, &mx, nullptr));
+        MM(phase_mark(c, MMD_PHASE_NEIGH));
       }
       const int ev = p->thermo_nstat > 0 ? ((n + 1) % p->thermo_nstat == 0) : 0;
       if (p->force_style == 0) MM(lj_async(c, p->halfneigh, p->ghost_newton, ev, true));
       else MM(eam_async(c, p->halfneigh, ev));
-      if (reverse_needed) MM(reverse(c));
+      MM(phase_mark(c, MMD_PHASE_FORCE));
+      if (reverse_needed) {
+        MM(reverse(c));
+        MM(phase_mark(c, MMD_PHASE_COMM));
+      }
       MM(final_(c, p->dtforce, ev != 0, p->mass));
+      MM(phase_mark(c, MMD_PHASE_INTEGRATE));
       if (ev) {
         MM(read_ev(c, 4));
         if (ns < max_samples && samples) {
@@ -841,6 +889,7 @@ template <class T> struct Impl {
       CU(cudaEventSynchronize(c->ev1));
       CU(cudaEventElapsedTime(elapsed_ms, c->ev0, c->ev1));
     }
+    MM(phase_collect(c));
     if (nsamples) *nsamples = ns;
     return MMD_OK;
   }
@@ -904,10 +953,10 @@ int mmd_ctx_create(int device, int precision_bytes, int ntypes, void* stream, mm
   }
   CU(cudaMalloc(&c->d_scal, 16 * sizeof(int)));
   CU(cudaMalloc(&c->d_total, sizeof(unsigned long long)));
-  CU(cudaMalloc(&c->d_ev, 4 * sizeof(double)));
+  CU(cudaMalloc(&c->d_ev, 32 * sizeof(double)));
   CU(cudaMemset(c->d_scal, 0, 16 * sizeof(int)));
   CU(cudaMemset(c->d_total, 0, sizeof(unsigned long long)));
-  CU(cudaMemset(c->d_ev, 0, 4 * sizeof(double)));
+  CU(cudaMemset(c->d_ev, 0, 32 * sizeof(double)));
   CU(cudaMallocHost(&c->h_scal, 16 * sizeof(int)));
   CU(cudaMallocHost(&c->h_total, sizeof(unsigned long long)));
   CU(cudaMallocHost(&c->h_ev, 4 * sizeof(double)));
@@ -936,6 +985,7 @@ int mmd_ctx_destroy(mmd_ctx* c) {
   cudaFree(c->d_scal); cudaFree(c->d_total); cudaFree(c->d_ev);
   cudaFreeHost(c->h_scal); cudaFreeHost(c->h_total); cudaFreeHost(c->h_ev);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  for (cudaEvent_t e : c->marks) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return MMD_OK;
@@ -1265,10 +1315,10 @@ int mmd_comm_sendlist_download(mmd_ctx* c, int iswap, int* list, int count) {
 }
 int mmd_comm_allreduce(mmd_ctx* c, double* values, int n, int op) {
   CHECK_CTX(c);
-  if (!values || n < 0 || n > 4) return set_err(MMD_ERR_ARG, "allreduce: n must be 0..4");
+  if (!values || n < 0 || n > 16) return set_err(MMD_ERR_ARG, "allreduce: n must be 0..16");
   if (c->nranks <= 1) return MMD_OK;
 #ifdef MMD_WITH_NCCL
-  double* d = c->d_ev;  // reuse the scalar block
+  double* d = c->d_ev + 8;  // upper part of the scalar block (the lower 8 belong to the kernels)
   CU(cudaMemcpyAsync(d, values, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   NC(ncclAllReduce(d, d, n, ncclDouble, op == 1 ? ncclMax : ncclSum, c->nccl, c->stream));
   CU(cudaMemcpyAsync(values, d, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1286,6 +1336,16 @@ int mmd_run(mmd_ctx* c, const mmd_run_params* p, mmd_thermo_sample* samples, int
   if (!p || p->ntimes < 0 || p->neigh_every < 1) return set_err(MMD_ERR_ARG, "run: bad parameters");
   return DISPATCH(c, Impl<double>::run(c, p, samples, max_samples, nsamples, elapsed_ms),
                   Impl<float>::run(c, p, samples, max_samples, nsamples, elapsed_ms));
+}
+
+int mmd_run_phase_times(mmd_ctx* c, double* ms, long long* calls, int reset) {
+  if (!c) return set_err(MMD_ERR_ARG, "null context");
+  for (int k = 0; k < MMD_NPHASE; k++) {
+    if (ms) ms[k] = c->phase_ms[k];
+    if (calls) calls[k] = c->phase_calls[k];
+    if (reset) { c->phase_ms[k] = 0; c->phase_calls[k] = 0; }
+  }
+  return MMD_OK;
 }
 
 // ---- introspection -------------------------------------------------------------------------
@@ -1327,6 +1387,8 @@ int mmd_set_option(mmd_ctx* c, const char* key, long long value) {
   } else if (k == "eam_threads_per_atom") {
     if (!pow2(value)) return set_err(MMD_ERR_ARG, "eam_threads_per_atom must be 1,2,4,8,16 or 32");
     c->eam_tpa = (int)value;
+  } else if (k == "phase_timing") {
+    c->phase_timing = value != 0;
   } else if (k == "force_nonuniform") {  // testing: exercise the per-type table path
     if (value) { c->lj_uniform = false; c->eam_uniform = false; }
   } else {
