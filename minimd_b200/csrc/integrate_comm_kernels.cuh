@@ -271,4 +271,69 @@ __global__ void border_unpack_kernel(Vec4<T>* __restrict__ x, int first, int n, 
   x[first + k] = p;
 }
 
+// ---- exchange: atom migration between sub-boxes (Comm::exchange, ref/comm.cpp:364-597) -----------
+// Leavers (x[dim] outside [lo,hi)) are packed in index order, 7 reals per atom (x,y,z,vx,vy,vz,type:
+// Atom::pack_exchange, ref/atom.cpp:228-240); the holes they leave below the new nlocal are filled, in
+// ascending order, with the surviving atoms of the tail -- the reference's hole-filling rule
+// (ref/comm.cpp:470-488).  Arrivals that fall inside my sub-box are appended in arrival order.
+template <class T>
+__global__ void exch_flag_kernel(const Vec4<T>* __restrict__ x, int n, int dim, T lo, T hi, int* __restrict__ leaves) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const T c = coord_of(x[i], dim);
+  leaves[i] = (c < lo || c >= hi) ? 1 : 0;
+}
+
+// pos = exclusive scan of leaves.  nkeep = n - (number of leavers).
+template <class T>
+__global__ void exch_pack_kernel(const Vec4<T>* __restrict__ x, const Vec4<T>* __restrict__ v, int n,
+                                 const int* __restrict__ leaves, const int* __restrict__ pos, int nkeep,
+                                 T* __restrict__ buf, int* __restrict__ hole_idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !leaves[i]) return;
+  const int r = pos[i];
+  const Vec4<T> xi = x[i], vi = v[i];
+  T* b = buf + (size_t)7 * r;
+  b[0] = xi.x; b[1] = xi.y; b[2] = xi.z;
+  b[3] = vi.x; b[4] = vi.y; b[5] = vi.z;
+  b[6] = (T)lane_to_type(xi.w);
+  if (i < nkeep) hole_idx[r] = i;  // every leaver before a hole is itself below nkeep, so r is the hole's rank
+}
+
+// survivors in [nkeep, n) move down into the holes; pos[nkeep] = number of holes
+template <class T>
+__global__ void exch_fill_kernel(Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ v, int n, const int* __restrict__ leaves,
+                                 const int* __restrict__ pos, int nkeep, const int* __restrict__ hole_idx) {
+  const int i = nkeep + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || leaves[i]) return;
+  const int nholes = pos[nkeep];
+  const int t = (i - nkeep) - (pos[i] - nholes);  // rank among the surviving tail atoms
+  const int dst = hole_idx[t];
+  x[dst] = x[i];
+  v[dst] = v[i];
+}
+
+template <class T>
+__global__ void exch_recv_flag_kernel(const T* __restrict__ buf, int n, int dim, T lo, T hi, int* __restrict__ mine) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const T c = buf[(size_t)7 * i + dim];
+  mine[i] = (c >= lo && c < hi) ? 1 : 0;
+}
+
+// Atom::unpack_exchange (ref/atom.cpp:242-254)
+template <class T>
+__global__ void exch_unpack_kernel(const T* __restrict__ buf, int n, const int* __restrict__ mine,
+                                   const int* __restrict__ pos, int first, Vec4<T>* __restrict__ x,
+                                   Vec4<T>* __restrict__ v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !mine[i]) return;
+  const T* b = buf + (size_t)7 * i;
+  Vec4<T> xi, vi;
+  xi.x = b[0]; xi.y = b[1]; xi.z = b[2]; xi.w = type_to_lane<T>((int)b[6]);
+  vi.x = b[3]; vi.y = b[4]; vi.z = b[5]; vi.w = (T)0;
+  x[first + pos[i]] = xi;
+  v[first + pos[i]] = vi;
+}
+
 }  // namespace mmd

@@ -156,6 +156,8 @@ struct mmd_ctx {
   SwapState sw[MMD_MAX_SWAPS];
   DevBuf border_tiles;  // 2 arrays of tile counts
   DevBuf sendbuf, recvbuf;
+  DevBuf exch_flag, exch_pos, exch_holes;
+  long long exch_sent = 0, exch_received = 0;  // atoms migrated so far (introspection)
 #ifdef MMD_WITH_NCCL
   ncclComm_t nccl = nullptr;
 #endif
@@ -894,10 +896,100 @@ template <class T> struct Impl {
     return MMD_OK;
   }
 
+  // exclusive scan of flags[0,n) into pos[0,n] (pos[n] = total); the total also lands in h_scal[5]
+  static int scan_flags(mmd_ctx* c, const int* flags, int n, int* pos, int* total) {
+    const int ntiles = std::max(1, div_up(n, SCAN_TILE));
+    MM(c->tile_sums.reserve((size_t)ntiles * sizeof(int), c->stream));
+    LAUNCH(c, scan_tile_sums_kernel, ntiles, SCAN_THREADS, flags, n, c->tile_sums.as<int>(), (int*)nullptr);
+    LAUNCH(c, scan_spine_kernel, 1, 1024, c->tile_sums.as<int>(), ntiles, pos + n, 0);
+    LAUNCH(c, scan_apply_kernel, ntiles, SCAN_THREADS, flags, n, c->tile_sums.as<int>(), pos);
+    CU(cudaMemcpyAsync(c->h_scal + 5, pos + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *total = c->h_scal[5];
+    return MMD_OK;
+  }
+
+  // Comm::exchange (ref/comm.cpp:364-597): wrap, then per decomposed dimension send every atom that left
+  // my sub-box to both neighbours and keep the arrivals that belong to me.
   static int exchange(mmd_ctx* c) {
     MM(pbc(c));
-    for (int d = 0; d < 3; d++)
-      if (c->swaps.procgrid[d] > 1) return set_err(MMD_ERR_STATE, "exchange across ranks is not implemented yet");
+    c->nghost = 0;  // ghosts are rebuilt by borders(); nlocal may change below
+    for (int d = 0; d < 3; d++) {
+      if (c->swaps.procgrid[d] <= 1) continue;
+#ifdef MMD_WITH_NCCL
+      if (!c->nccl) return set_err(MMD_ERR_STATE, "exchange across ranks requested but mmd_comm_nccl_init was not called");
+      const T lo = (T)c->lo[d], hi = (T)c->hi[d];
+      const int n = c->nlocal;
+      const int lower = c->swaps.procneigh[d][0], upper = c->swaps.procneigh[d][1];
+      const bool both = c->swaps.procgrid[d] > 2;
+      MM(c->exch_flag.reserve((size_t)(n + 2) * sizeof(int), c->stream, 0, 1.2));
+      MM(c->exch_pos.reserve((size_t)(n + 2) * sizeof(int), c->stream, 0, 1.2));
+      int nsend = 0;
+      if (n > 0) {
+        LAUNCH(c, exch_flag_kernel<T>, div_up(n, TPB), TPB, c->x.as<V>(), n, d, lo, hi, c->exch_flag.as<int>());
+        MM(scan_flags(c, c->exch_flag.as<int>(), n, c->exch_pos.as<int>(), &nsend));
+      }
+      const int nkeep = n - nsend;
+      if (nsend > 0) {
+        MM(c->sendbuf.reserve((size_t)7 * nsend * sizeof(T), c->stream, 0, 1.5));
+        MM(c->exch_holes.reserve((size_t)nsend * sizeof(int), c->stream, 0, 1.5));
+        LAUNCH(c, exch_pack_kernel<T>, div_up(n, TPB), TPB, c->x.as<V>(), c->v.as<V>(), n, c->exch_flag.as<int>(),
+               c->exch_pos.as<int>(), nkeep, c->sendbuf.as<T>(), c->exch_holes.as<int>());
+        if (nkeep < n)
+          LAUNCH(c, exch_fill_kernel<T>, div_up(n - nkeep, TPB), TPB, c->x.as<V>(), c->v.as<V>(), n, c->exch_flag.as<int>(),
+                 c->exch_pos.as<int>(), nkeep, c->exch_holes.as<int>());
+      }
+      c->nlocal = nkeep;
+      c->exch_sent += nsend;
+      // counts (ref/comm.cpp:521-530), then payloads (:535-544)
+      int* d_cnt = c->d_scal + 6;  // [6] my count, [8] from upper, [9] from lower
+      c->h_scal[6] = nsend;
+      c->h_scal[8] = c->h_scal[9] = 0;
+      CU(cudaMemcpyAsync(d_cnt, c->h_scal + 6, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+      CU(cudaMemsetAsync(d_cnt + 2, 0, 2 * sizeof(int), c->stream));
+      NC(ncclGroupStart());
+      NC(ncclSend(d_cnt, 1, ncclInt, lower, c->nccl, c->stream));
+      NC(ncclRecv(d_cnt + 2, 1, ncclInt, upper, c->nccl, c->stream));
+      if (both) {
+        NC(ncclSend(d_cnt, 1, ncclInt, upper, c->nccl, c->stream));
+        NC(ncclRecv(d_cnt + 3, 1, ncclInt, lower, c->nccl, c->stream));
+      }
+      NC(ncclGroupEnd());
+      CU(cudaMemcpyAsync(c->h_scal + 8, d_cnt + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      const int nrecv1 = c->h_scal[8], nrecv2 = both ? c->h_scal[9] : 0;
+      const int nrecv = nrecv1 + nrecv2;
+      MM(c->recvbuf.reserve((size_t)7 * std::max(nrecv, 1) * sizeof(T), c->stream, 0, 1.5));
+      T* r1 = c->recvbuf.as<T>();
+      T* r2 = r1 + (size_t)7 * nrecv1;
+      NC(ncclGroupStart());
+      if (nsend) NC(ncclSend(c->sendbuf.p, (size_t)7 * nsend, nccl_real(), lower, c->nccl, c->stream));
+      if (nrecv1) NC(ncclRecv(r1, (size_t)7 * nrecv1, nccl_real(), upper, c->nccl, c->stream));
+      if (both) {
+        if (nsend) NC(ncclSend(c->sendbuf.p, (size_t)7 * nsend, nccl_real(), upper, c->nccl, c->stream));
+        if (nrecv2) NC(ncclRecv(r2, (size_t)7 * nrecv2, nccl_real(), lower, c->nccl, c->stream));
+      }
+      NC(ncclGroupEnd());
+      if (nrecv > 0) {
+        MM(c->exch_flag.reserve((size_t)(nrecv + 2) * sizeof(int), c->stream, 0, 1.2));
+        MM(c->exch_pos.reserve((size_t)(nrecv + 2) * sizeof(int), c->stream, 0, 1.2));
+        LAUNCH(c, exch_recv_flag_kernel<T>, div_up(nrecv, TPB), TPB, c->recvbuf.as<T>(), nrecv, d, lo, hi,
+               c->exch_flag.as<int>());
+        int nmine = 0;
+        MM(scan_flags(c, c->exch_flag.as<int>(), nrecv, c->exch_pos.as<int>(), &nmine));
+        if (nmine > 0) {
+          MM(reserve_atoms(c, c->nlocal + nmine));
+          LAUNCH(c, exch_unpack_kernel<T>, div_up(nrecv, TPB), TPB, c->recvbuf.as<T>(), nrecv, c->exch_flag.as<int>(),
+                 c->exch_pos.as<int>(), c->nlocal, c->x.as<V>(), c->v.as<V>());
+          c->nlocal += nmine;
+          c->exch_received += nmine;
+        }
+      }
+#else
+      return set_err(MMD_ERR_STATE, "exchange across ranks requested but the library was built without NCCL");
+#endif
+    }
+    c->neigh_rows = -1;
     return MMD_OK;
   }
 };
@@ -976,7 +1068,8 @@ int mmd_ctx_destroy(mmd_ctx* c) {
                     &c->runs, &c->cutneighsq, &c->atom_bin, &c->bin_atoms, &c->bincount, &c->bin_start, &c->cursor,
                     &c->tile_sums, &c->numneigh, &c->neighbors, &c->lj_cut, &c->lj_s6, &c->lj_eps, &c->eam_rho_val,
                     &c->eam_rho_der, &c->eam_z2_val, &c->eam_z2_der, &c->eam_frho_val, &c->eam_frho_der, &c->eam_cut,
-                    &c->rho, &c->fp, &c->border_tiles, &c->sendbuf, &c->recvbuf};
+                    &c->rho, &c->fp, &c->border_tiles, &c->sendbuf, &c->recvbuf, &c->exch_flag, &c->exch_pos,
+                    &c->exch_holes};
   for (DevBuf* b : bufs) b->release();
   for (int w = 0; w < MMD_MAX_SWAPS; w++) c->sw[w].list.release();
 #ifdef MMD_WITH_NCCL
@@ -1373,6 +1466,9 @@ int mmd_query_int(mmd_ctx* c, const char* key, long long* value) {
   else if (k == "lj_threads_per_atom") *value = c->lj_tpa;
   else if (k == "eam_threads_per_atom") *value = c->eam_tpa;
   else if (k == "launches") *value = c->launches;
+  else if (k == "exchange_sent") *value = c->exch_sent;
+  else if (k == "exchange_received") *value = c->exch_received;
+  else if (k == "nranks") *value = c->nranks;
   else return set_err(MMD_ERR_ARG, "query: unknown key '%s'", key);
   return MMD_OK;
 }

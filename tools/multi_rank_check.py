@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check, run under torchrun (one rank per GPU):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/multi_rank_check.py
+Runs the same deck on N ranks through the host layer (NCCL halo swaps, migration, ghost rebuild on
+the device) and compares T/U/P at every thermo step, atom conservation and neighbor totals with the
+single-rank oracle.  Rank 0 prints one JSON line; exit code 0 = parity."""
+import argparse
+import json
+import os
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cells", type=int, nargs=3, default=[16, 16, 16])
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--force", default="lj")
+    ap.add_argument("--half_neigh", type=int, default=1)
+    ap.add_argument("--ghost_newton", type=int, default=1)
+    ap.add_argument("--precision", default="f64")
+    ap.add_argument("--tol", type=float, default=1e-9)
+    a = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from helpers import eam_file
+    from minimd_b200 import Simulation, nccl_unique_id
+    from oracle.oracle import Config, Oracle
+
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(idt, 0)
+    cfg = Config(nx=a.cells[0], ny=a.cells[1], nz=a.cells[2], ntimes=a.steps, force=a.force, halfneigh=a.half_neigh,
+                 ghost_newton=a.ghost_newton, thermo_nstat=10)
+    with tempfile.TemporaryDirectory() as td:
+        deck = os.path.join(td, f"in.{rank}")
+        open(deck, "w").write(cfg.input_text())
+        args = ["-i", deck, "--half_neigh", a.half_neigh, "-gn", a.ghost_newton, "--quiet"]
+        if a.force == "eam":
+            args += ["--eam_file", eam_file(td)]
+        sim = Simulation(args, a.precision, rank=rank, nranks=world, device=local, nccl_id=idt.cpu().numpy().tobytes())
+        neigh0 = torch.tensor([sim.geti("total_neigh")], dtype=torch.float64, device="cuda")
+        dist.all_reduce(neigh0)
+        ms = sim.run()
+        st, T, U, P = sim.thermo()
+        cnt = torch.tensor([sim.geti("nlocal"), sim.geti("total_neigh"), sim.geti("nghost"),
+                            sim.context().query("exchange_sent")], dtype=torch.float64, device="cuda")
+        dist.all_reduce(cnt)
+        grid = [sim.geti(f"procgrid{d}") for d in range(3)]
+        sim.close()
+    ok, res = True, None
+    if rank == 0:
+        o = Oracle(cfg, "f64")
+        n0 = int(o.numneigh().sum())
+        o.run(a.steps)
+        so, To, Uo, Po = o.thermo_log()
+        rel = lambda x, y: float(np.max(np.abs(np.array(x) - np.array(y)) / np.maximum(np.abs(np.array(y)), 1e-300)))
+        pscale = max(1.0, float(np.max(np.abs(Po))))
+        errs = {"T": rel(T, To), "U": rel(U, Uo), "P": float(np.max(np.abs(np.array(P) - np.array(Po))) / pscale)}
+        n1 = int(o.numneigh().sum())
+        ok = (list(st) == list(so) and errs["T"] < a.tol and errs["U"] < a.tol and errs["P"] < 10 * a.tol
+              and int(cnt[0].item()) == o.geti("natoms") and int(neigh0.item()) == n0 and abs(int(cnt[1].item()) - n1) <= 16)
+        res = {"ok": bool(ok), "ranks": world, "procgrid": grid, "cells": a.cells, "force": a.force, "errs": errs,
+               "natoms": int(cnt[0].item()), "neigh_step0": [int(neigh0.item()), n0], "neigh_end": [int(cnt[1].item()), n1],
+               "nghost_sum": int(cnt[2].item()), "migrated_atoms": int(cnt[3].item()), "device_ms": ms,
+               "last": [st[-1], T[-1], U[-1], P[-1]]}
+        print(json.dumps(res), flush=True)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()
