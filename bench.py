@@ -83,7 +83,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True,
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True,
                                          stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
@@ -396,7 +396,7 @@ def own_arm(a, n_gpus, rank, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--size", type=int, default=CELLS_PER_GPU, help="unit cells per GPU edge (the metric is quoted at 80)")

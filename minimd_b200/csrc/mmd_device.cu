@@ -142,7 +142,7 @@ struct mmd_ctx {
   bool have_lj = false, lj_uniform = true;
   DevBuf lj_cut, lj_s6, lj_eps;
   double lj_cut0 = 0, lj_s60 = 0, lj_eps0 = 0;
-  int lj_tpa = 8;
+  int lj_tpa = 0;  // lanes per atom in the LJ kernels; 0 = auto (half list 2, full list 4: profiles/r1_ncu_force_neigh_lj80.md)
   bool have_eam = false, eam_uniform = true;
   DevBuf eam_rho_val, eam_rho_der, eam_z2_val, eam_z2_der, eam_frho_val, eam_frho_der, eam_cut;
   double eam_cut0 = 0, eam_rdr = 0, eam_rdrho = 0;
@@ -491,7 +491,7 @@ template <class T> struct Impl {
     if (c->neigh_rows != c->nlocal) return set_err(MMD_ERR_STATE, "force_lj: neighbor list is stale (build first)");
     if (half && clear_f) CU(cudaMemsetAsync(c->f.p, 0, (size_t)(c->nlocal + c->nghost) * sizeof(V), c->stream));
     if (ev) CU(cudaMemsetAsync(c->d_ev, 0, 2 * sizeof(double), c->stream));
-    switch (c->lj_tpa) {
+    switch (c->lj_tpa ? c->lj_tpa : (half ? 2 : 4)) {
       case 1: return lj_dispatch<1>(c, half, gn, ev);
       case 2: return lj_dispatch<2>(c, half, gn, ev);
       case 4: return lj_dispatch<4>(c, half, gn, ev);
@@ -1478,7 +1478,7 @@ int mmd_set_option(mmd_ctx* c, const char* key, long long value) {
   std::string k(key);
   auto pow2 = [](long long v) { return v >= 1 && v <= 32 && (v & (v - 1)) == 0; };
   if (k == "lj_threads_per_atom") {
-    if (!pow2(value)) return set_err(MMD_ERR_ARG, "lj_threads_per_atom must be 1,2,4,8,16 or 32");
+    if (value != 0 && !pow2(value)) return set_err(MMD_ERR_ARG, "lj_threads_per_atom must be 0 (auto),1,2,4,8,16 or 32");
     c->lj_tpa = (int)value;
   } else if (k == "eam_threads_per_atom") {
     if (!pow2(value)) return set_err(MMD_ERR_ARG, "eam_threads_per_atom must be 1,2,4,8,16 or 32");

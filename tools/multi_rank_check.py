@@ -68,8 +68,14 @@ def main():
         pscale = max(1.0, float(np.max(np.abs(Po))))
         errs = {"T": rel(T, To), "U": rel(U, Uo), "P": float(np.max(np.abs(np.array(P) - np.array(Po))) / pscale)}
         n1 = int(o.numneigh().sum())
+        # half list without ghost_newton stores a cross-rank pair on BOTH owners (each updates only its own atom),
+        # so its total grows with the rank-boundary surface; the other styles store every pair a fixed number of times
+        gn_eff = a.ghost_newton if a.force == "lj" else 0
+        decomposition_invariant = not (a.half_neigh and not gn_eff)
+        counts_ok = (int(neigh0.item()) == n0 and abs(int(cnt[1].item()) - n1) <= 16) if decomposition_invariant \
+            else (int(neigh0.item()) >= n0 and int(cnt[1].item()) >= n1 - 16)
         ok = (list(st) == list(so) and errs["T"] < a.tol and errs["U"] < a.tol and errs["P"] < 10 * a.tol
-              and int(cnt[0].item()) == o.geti("natoms") and int(neigh0.item()) == n0 and abs(int(cnt[1].item()) - n1) <= 16)
+              and int(cnt[0].item()) == o.geti("natoms") and counts_ok)
         res = {"ok": bool(ok), "ranks": world, "procgrid": grid, "cells": a.cells, "force": a.force, "errs": errs,
                "natoms": int(cnt[0].item()), "neigh_step0": [int(neigh0.item()), n0], "neigh_end": [int(cnt[1].item()), n1],
                "nghost_sum": int(cnt[2].item()), "migrated_atoms": int(cnt[3].item()), "device_ms": ms,
