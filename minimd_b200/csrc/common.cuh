@@ -62,6 +62,43 @@ __device__ __forceinline__ void red_add1(float* p, float a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Warp-cooperative force scatter for FP64 (half neighbor lists).
+// Measured on B200 (tools/microbench/red_bench.cu): RED.E.ADD.F64 throughput is ~222 G
+// instruction-lanes/s when every lane of an instruction targets its own 32-byte sector, but lanes of
+// ONE instruction that fall into the same sector are merged: emitting x,y,z of an atom from three
+// adjacent lanes of a single RED moves 2.3x more pair updates per second than three separate
+// REDs per lane.  So the 32 (fx,fy,fz,j) records of a warp are transposed through shared memory
+// into 96 (address, value) elements and emitted as 3 RED instructions of 32 lanes, 3 lanes per atom.
+// Must be called by all 32 lanes (warp-uniform control flow); `on` selects the lanes that contribute.
+// sv: 96 doubles, sj: 32 ints of shared memory private to the calling warp.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_scatter3(Vec4<double>* __restrict__ f, double* sv, int* sj, int lane, bool on,
+                                              int j, double a, double b, double c) {
+  const unsigned mask = __ballot_sync(0xffffffffu, on);
+  if (mask == 0u) return;
+  if (on) {
+    sv[3 * lane + 0] = a;
+    sv[3 * lane + 1] = b;
+    sv[3 * lane + 2] = c;
+    sj[lane] = j;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    const int e = 32 * r + lane;
+    const int p = e / 3;
+    const int comp = e - 3 * p;
+    if ((mask >> p) & 1u) red_add1(reinterpret_cast<double*>(f + sj[p]) + comp, sv[e]);
+  }
+  __syncwarp();
+}
+// FP32: one 128-bit vector reduction per pair already covers the whole atom record
+__device__ __forceinline__ void warp_scatter3(Vec4<float>* __restrict__ f, float*, int*, int, bool on, int j, float a,
+                                              float b, float c) {
+  if (on) red_add3(f + j, a, b, c);
+}
+
+// ---------------------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------------------
 template <int WIDTH, class T> __device__ __forceinline__ T group_sum(T v) {

@@ -37,18 +37,35 @@ force_lj_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, const in
   const int gtid = blockIdx.x * LJ_BLOCK + threadIdx.x;
   const int i = gtid / TPA;
   const int sub = threadIdx.x % TPA;
+  const int lane = threadIdx.x & 31;
   const bool active = i < nlocal;
+  // staging area of the warp-cooperative scatter (half lists only; unused and not allocated otherwise)
+  __shared__ T s_val[HALF ? LJ_BLOCK / 32 : 1][HALF ? 96 : 1];
+  __shared__ int s_idx[HALF ? LJ_BLOCK / 32 : 1][HALF ? 32 : 1];
+  T* sv = s_val[HALF ? (threadIdx.x >> 5) : 0];
+  int* sj = s_idx[HALF ? (threadIdx.x >> 5) : 0];
 
   T fx = 0, fy = 0, fz = 0;
   double eng = 0.0, vir = 0.0;
 
+  Vec4<T> xi;
+  xi.x = xi.y = xi.z = xi.w = (T)0;
+  int cnt = 0;
+  const int* __restrict__ row = neighbors + (size_t)(active ? i : 0) * stride;
   if (active) {
-    const Vec4<T> xi = x[i];
-    const int ti = lane_to_type(xi.w);
-    const int* __restrict__ row = neighbors + (size_t)i * stride;
-    const int cnt = numneigh[i];
-    for (int k = sub; k < cnt; k += TPA) {
-      const int j = __ldg(row + k);
+    xi = x[i];
+    cnt = numneigh[i];
+  }
+  const int ti = lane_to_type(xi.w);
+  // half lists: every lane of the warp runs the same number of iterations (the scatter is warp-cooperative)
+  const int kend = HALF ? __reduce_max_sync(0xffffffffu, cnt) : cnt;
+  for (int k0 = 0; k0 < kend; k0 += TPA) {
+    const int k = k0 + sub;
+    bool scatter = false;
+    int j = 0;
+    T sx = 0, sy = 0, sz = 0;
+    if (k < cnt) {
+      j = __ldg(row + k);
       const Vec4<T> xj = ldg4(x + j);
       const T dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
       const T rsq = dx * dx + dy * dy + dz * dz;
@@ -67,8 +84,8 @@ force_lj_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, const in
         fy += dy * force;
         fz += dz * force;
         if (HALF) {
-          const bool scatter = GN || (j < nlocal);
-          if (scatter) red_add3(f + j, -dx * force, -dy * force, -dz * force);
+          scatter = GN || (j < nlocal);
+          sx = -dx * force; sy = -dy * force; sz = -dz * force;
           if (EV) {
             const double scale = scatter ? 1.0 : 0.5;
             eng += scale * (double)((T)4 * sr6 * (sr6 - (T)1) * eps);
@@ -80,20 +97,19 @@ force_lj_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, const in
         }
       }
     }
+    if (HALF) warp_scatter3(f, sv, sj, lane, scatter, j, sx, sy, sz);
   }
   if (TPA > 1) {
     fx = group_sum<TPA>(fx);
     fy = group_sum<TPA>(fy);
     fz = group_sum<TPA>(fz);
   }
-  if (active && sub == 0) {
-    if (HALF) {
-      red_add3(f + i, fx, fy, fz);
-    } else {
-      Vec4<T> out;
-      out.x = fx; out.y = fy; out.z = fz; out.w = (T)0;
-      f[i] = out;
-    }
+  if (HALF) {
+    warp_scatter3(f, sv, sj, lane, active && sub == 0, i, fx, fy, fz);
+  } else if (active && sub == 0) {
+    Vec4<T> out;
+    out.x = fx; out.y = fy; out.z = fz; out.w = (T)0;
+    f[i] = out;
   }
   if (EV) {
     if (!HALF) { eng *= 4.0; vir *= 0.5; }  // ref/force_lj.cpp:441-442

@@ -9,11 +9,12 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this.  It is the CHECKER for the CUDA path in minimd_b200/csrc, nothing else.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks this file's T/U/P at
- * every step against the unmodified reference binary (oracle/_ref/, built by
- * oracle/build_ref.sh from /root/reference) and tests/test_oracle_golden.py checks it
- * against the reference's shipped logs tests/reference_output/{4k,16k,32k}.{lj,eam}
- * (committed as tests/golden/reference_logs.json).
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks this file's T/U/P (a) at every
+ * step against a live run of the unmodified reference binary (oracle/_ref/, built by
+ * oracle/build_ref.sh from /root/reference), (b) against 10-digit outputs of that binary on
+ * BASELINE.json's configurations (tests/golden/reference_runs.json, made by
+ * tests/golden/make_golden.py) and (c) against the reference's shipped logs
+ * tests/reference_output/{4k,16k,32k}.{lj,eam} (committed as tests/golden/reference_logs.json).
  *
  * Arithmetic is kept in the reference's evaluation order (serial, no FMA contraction: build
  * with -ffp-contract=off, matching the reference's g++ -O3 -mavx build) so that single-thread
