@@ -1,7 +1,16 @@
 #include "setup.h"
 
+#include "comm.h"
+#include "integrate.h"
+#include "neighbor.h"
+
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
 
 #include <algorithm>
 
@@ -96,4 +105,126 @@ void create_velocity(double t_request, Atom& atom, Thermo& thermo, World& world)
   const double factor = sqrt(t_request / temp);
   for (int i = 0; i < atom.nlocal; i++)
     for (int c = 0; c < 3; c++) atom.v[i * PAD + c] *= factor;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LAMMPS data file
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+bool blank(const std::string& s) { return s.find_first_not_of(" \t\n\r") == std::string::npos; }
+
+std::string trimmed(const std::string& s) {
+  const size_t a = s.find_first_not_of(" \t\n\r");
+  if (a == std::string::npos) return "";
+  const size_t b = s.find_last_not_of(" \t\n\r");
+  return s.substr(a, b - a + 1);
+}
+
+bool next_line(FILE* fp, std::string& out) {
+  char buf[512];
+  if (!fgets(buf, sizeof buf, fp)) return false;
+  out = buf;
+  return true;
+}
+
+}  // namespace
+
+int read_lammps_data(Atom& atom, Comm& comm, Neighbor& neighbor, Integrate& integrate, Thermo& thermo, const char* file,
+                     int units, World& world) {
+  FILE* fp = fopen(file, "r");
+  if (!fp) {
+    if (world.me == 0) printf("ERROR: Cannot open file %s\n", file);
+    return 1;
+  }
+  std::string line;
+  next_line(fp, line);  // title
+
+  // header: "<n> atoms", "<n> atom types", "<lo> <hi> xlo xhi" ...; anything after '#' is a comment.
+  // As in the reference only the box LENGTHS are used (the box is taken to start at the origin).
+  std::string section;
+  atom.natoms = 0;
+  while (next_line(fp, line)) {
+    const size_t hash = line.find('#');
+    if (hash != std::string::npos) line.erase(hash);
+    if (blank(line)) continue;
+    double lo = 0, hi = 0;
+    if (line.find("atom types") != std::string::npos) continue;
+    if (line.find("atoms") != std::string::npos) sscanf(line.c_str(), "%i", &atom.natoms);
+    else if (line.find("xlo xhi") != std::string::npos) { sscanf(line.c_str(), "%lg %lg", &lo, &hi); atom.box.xprd = hi - lo; }
+    else if (line.find("ylo yhi") != std::string::npos) { sscanf(line.c_str(), "%lg %lg", &lo, &hi); atom.box.yprd = hi - lo; }
+    else if (line.find("zlo zhi") != std::string::npos) { sscanf(line.c_str(), "%lg %lg", &lo, &hi); atom.box.zprd = hi - lo; }
+    else { section = trimmed(line); break; }
+  }
+  if (atom.natoms <= 0 || !(atom.box.xprd > 0 && atom.box.yprd > 0 && atom.box.zprd > 0)) {
+    if (world.me == 0) printf("ERROR: bad header in data file %s\n", file);
+    fclose(fp);
+    return 1;
+  }
+
+  if (comm.setup(neighbor.cutneigh, atom)) { fclose(fp); return 1; }
+  if (neighbor.nbinx < 0) {  // no -b: about 16 atoms per 2x2x2 bins (ref/setup.cpp:226-233)
+    const MMD_float volume = atom.box.xprd * atom.box.yprd * atom.box.zprd;
+    const MMD_float rho = 1.0 * atom.natoms / volume;
+    const MMD_float neigh_bin_size = pow(rho * 16, MMD_float(1.0 / 3.0));
+    neighbor.nbinx = atom.box.xprd / neigh_bin_size;
+    neighbor.nbiny = atom.box.yprd / neigh_bin_size;
+    neighbor.nbinz = atom.box.zprd / neigh_bin_size;
+  }
+  if (neighbor.nbinx == 0) neighbor.nbinx = 1;
+  if (neighbor.nbiny == 0) neighbor.nbiny = 1;
+  if (neighbor.nbinz == 0) neighbor.nbinz = 1;
+  if (neighbor.setup(atom)) { fclose(fp); return 1; }
+  integrate.setup();
+  thermo.setup(atom.box.xprd * atom.box.yprd * atom.box.zprd / atom.natoms, integrate, atom, units);
+
+  std::vector<MMD_float> x((size_t)atom.natoms * 3, 0), v((size_t)atom.natoms * 3, 0);
+  bool have_atoms = false;
+  while (!section.empty()) {
+    next_line(fp, line);  // the blank line under the section keyword
+    if (section == "Atoms" || section == "Velocities") {
+      const bool pos = section == "Atoms";
+      if (!pos && !have_atoms && world.me == 0) printf("Must read Atoms before Velocities\n");
+      std::vector<MMD_float>& dst = pos ? x : v;
+      for (int nread = 0; nread < atom.natoms; nread++) {
+        if (!next_line(fp, line)) break;
+        int id = 0, type = 0;
+        double a = 0, b = 0, c = 0;
+        if (pos) sscanf(line.c_str(), "%i %i %lg %lg %lg", &id, &type, &a, &b, &c);
+        else sscanf(line.c_str(), "%i %lg %lg %lg", &id, &a, &b, &c);
+        if (id < 1 || id > atom.natoms) continue;
+        dst[(size_t)(id - 1) * 3 + 0] = a;
+        dst[(size_t)(id - 1) * 3 + 1] = b;
+        dst[(size_t)(id - 1) * 3 + 2] = c;
+      }
+      if (pos) have_atoms = true;
+    } else if (section == "Masses") {
+      if (next_line(fp, line)) {
+        int t = 0;
+        double m = 0;
+        if (sscanf(line.c_str(), "%i %lg", &t, &m) == 2) atom.mass = m;
+      }
+      while (next_line(fp, line) && !blank(line)) {}  // further types (all atoms share one mass in miniMD)
+    }
+    // next section keyword = next non-blank line
+    section.clear();
+    while (next_line(fp, line)) {
+      if (!blank(line)) { section = trimmed(line); break; }
+    }
+  }
+  fclose(fp);
+
+  atom.nlocal = 0;
+  for (int i = 0; i < atom.natoms; i++) {
+    const MMD_float* p = &x[(size_t)i * 3];
+    if (p[0] >= atom.box.xlo && p[0] < atom.box.xhi && p[1] >= atom.box.ylo && p[1] < atom.box.yhi &&
+        p[2] >= atom.box.zlo && p[2] < atom.box.zhi)
+      atom.addatom(p[0], p[1], p[2], v[(size_t)i * 3 + 0], v[(size_t)i * 3 + 1], v[(size_t)i * 3 + 2]);
+  }
+  const long long natoms = world.sum_ll(atom.nlocal);
+  if (natoms != atom.natoms) {
+    if (world.me == 0) printf("Created incorrect # of atoms\n");
+    return 1;
+  }
+  return 0;
 }

@@ -106,11 +106,6 @@ int Simulation::init(const Options& o, const World& w, const unsigned char* nccl
   if (!opt.datafile.empty()) in.datafile = opt.datafile;
   if (opt.units >= 0) in.units = opt.units;
   if (opt.forcetype >= 0) in.forcetype = (ForceStyle)opt.forcetype;
-  if (!in.datafile.empty()) {
-    error = "LAMMPS data files (-f / input line 4) are not supported yet";
-    if (out()) printf("ERROR: %s\n", error.c_str());
-    return 1;
-  }
 
   // device context of this rank
   const int device = opt.device >= 0 ? opt.device : world.device;
@@ -170,9 +165,11 @@ int Simulation::init(const Options& o, const World& w, const unsigned char* nccl
     if (opt.nz > 0) in.nz = opt.nz;
     else if (opt.system_size < 0) in.nz = opt.nx;
   }
-  // 5 bins per 6 lattice cells unless -b (ref/ljs.cpp:351-368)
+  // 5 bins per 6 lattice cells unless -b (ref/ljs.cpp:351-368); with a data file the bin count comes from the density
   if (opt.neighbor_size > 0) {
     neighbor->nbinx = neighbor->nbiny = neighbor->nbinz = opt.neighbor_size;
+  } else if (!in.datafile.empty()) {
+    neighbor->nbinx = neighbor->nbiny = neighbor->nbinz = -1;
   } else {
     MMD_float neighscale = 5.0 / 6.0;
     neighbor->nbinx = neighscale * in.nx;
@@ -182,6 +179,7 @@ int Simulation::init(const Options& o, const World& w, const unsigned char* nccl
   if (neighbor->nbinx == 0) neighbor->nbinx = 1;
   if (neighbor->nbiny == 0) neighbor->nbiny = 1;
   if (neighbor->nbinz == 0) neighbor->nbinz = 1;
+  // (with a data file and no -b, nbinx is -1 here and nbiny/nbinz follow in read_lammps_data)
 
   integrate.ntimes = in.ntimes;
   integrate.dt = in.dt;
@@ -193,15 +191,26 @@ int Simulation::init(const Options& o, const World& w, const unsigned char* nccl
   thermo.nstat = in.thermo_nstat;
 
   if (out()) printf("# Create System:\n");
-  create_box(*atom, in.nx, in.ny, in.nz, in.rho);
-  if (comm.setup(neighbor->cutneigh, *atom)) { error = "Comm::setup failed"; return 1; }
-  if (neighbor->setup(*atom)) { error = "Neighbor::setup failed"; return 1; }
-  integrate.setup();
-  if (force->setup(*atom)) { error = "Force::setup failed"; return 1; }
-  if (in.forcetype == FORCEEAM) atom->mass = force->mass;
-  if (create_atoms(*atom, in.nx, in.ny, in.nz, in.rho, world)) { error = "create_atoms failed"; return 1; }
-  thermo.setup(in.rho, integrate, *atom, in.units);
-  create_velocity(in.t_request, *atom, thermo, world);
+  if (!in.datafile.empty()) {  // ref/ljs.cpp:382-390
+    if (read_lammps_data(*atom, comm, *neighbor, integrate, thermo, in.datafile.c_str(), in.units, world)) {
+      error = "read_lammps_data failed for " + in.datafile;
+      return 1;
+    }
+    const MMD_float volume = atom->box.xprd * atom->box.yprd * atom->box.zprd;
+    in.rho = 1.0 * atom->natoms / volume;
+    if (force->setup(*atom)) { error = "Force::setup failed"; return 1; }
+    if (in.forcetype == FORCEEAM) atom->mass = force->mass;
+  } else {
+    create_box(*atom, in.nx, in.ny, in.nz, in.rho);
+    if (comm.setup(neighbor->cutneigh, *atom)) { error = "Comm::setup failed"; return 1; }
+    if (neighbor->setup(*atom)) { error = "Neighbor::setup failed"; return 1; }
+    integrate.setup();
+    if (force->setup(*atom)) { error = "Force::setup failed"; return 1; }
+    if (in.forcetype == FORCEEAM) atom->mass = force->mass;
+    if (create_atoms(*atom, in.nx, in.ny, in.nz, in.rho, world)) { error = "create_atoms failed"; return 1; }
+    thermo.setup(in.rho, integrate, *atom, in.units);
+    create_velocity(in.t_request, *atom, thermo, world);
+  }
   if (host_only) return 0;
   if (atom->upload()) { error = mmd_last_error(); return 1; }
   if (out()) printf("# Done .... \n");

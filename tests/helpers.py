@@ -113,3 +113,36 @@ def rel(a, b):
 def g6(v):
     """A count as the reference's YAML/histogram report prints it (%g, ref/output.cpp:402-481)."""
     return int(float(f"{float(v):.6g}"))
+
+
+def write_lammps_data(path, x, v, prd, mass=1.0):
+    """A LAMMPS data file in the layout the reference's reader expects (ref/setup.cpp:54-301):
+    header counts + box bounds, then Masses / Atoms ('id type x y z') / Velocities ('id vx vy vz')."""
+    with open(path, "w") as fh:
+        fh.write("LAMMPS data file written by tests/helpers.py\n\n")
+        fh.write(f"{len(x)} atoms\n1 atom types\n\n")
+        for d, name in enumerate("xyz"):
+            fh.write(f"0.0 {float(prd[d])!r} {name}lo {name}hi\n")
+        fh.write("\nMasses\n\n")
+        fh.write(f"1 {float(mass)!r}\n")
+        fh.write("\nAtoms\n\n")
+        for i, r in enumerate(x):
+            fh.write(f"{i + 1} 1 {float(r[0])!r} {float(r[1])!r} {float(r[2])!r}\n")
+        fh.write("\nVelocities\n\n")
+        for i, r in enumerate(v):
+            fh.write(f"{i + 1} {float(r[0])!r} {float(r[1])!r} {float(r[2])!r}\n")
+    return path
+
+
+def lattice_for_datafile(cells=6, jitter=0.05, seed=11):
+    """Deterministic non-trivial configuration: the synthetic FCC lattice of the host layer, every atom
+    displaced by a small seeded offset (so the data-file run differs from the built-in lattice run)."""
+    from minimd_b200 import Simulation, input_file
+    s = Simulation.plan(["-i", input_file("in.lj.miniMD"), "-s", str(cells)])
+    x = s.host_array("x").reshape(-1, 3).copy()
+    v = s.host_array("v").reshape(-1, 3).copy()
+    prd = np.array([s.getr("xprd"), s.getr("yprd"), s.getr("zprd")])
+    rng = np.random.default_rng(seed)
+    x = np.mod(x + rng.uniform(-jitter, jitter, x.shape), prd)
+    x = np.minimum(x, np.nextafter(prd, 0))
+    return x, v, prd

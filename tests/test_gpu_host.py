@@ -171,3 +171,17 @@ def test_driver_fp32_and_help(tmp_path):
     assert h.returncode == 0 and "--half_neigh" in h.stdout
     bad = run_driver("f64", ["-i", "no_such_file"], str(tmp_path))
     assert bad.returncode != 0 and "Cannot open" in (bad.stdout + bad.stderr)
+
+
+@pytest.mark.parametrize("name", ["lj_data_half", "lj_data_full"])
+def test_lammps_data_file_run_matches_reference_binary(name, tmp_path):
+    """Start from a LAMMPS data file (the reference's alternative input path, ref/setup.cpp:215-301)."""
+    from helpers import lattice_for_datafile, write_lammps_data
+    g = golden("reference_datafile.json")[name]
+    x, v, prd = lattice_for_datafile()
+    data = write_lammps_data(str(tmp_path / "atoms.data"), x, v, prd)
+    cfg = Config(nx=6, ny=6, nz=6, ntimes=100, halfneigh=g["half"], ghost_newton=g["gn"], thermo_nstat=10)
+    sim = Simulation(args_for(tmp_path, cfg, ["-f", data]), "f64")
+    sim.run()
+    check_thermo(sim, g, 1e-9)
+    assert (sim.geti("nlocal"), sim.geti("nghost"), sim.geti("total_neigh")) == (g["nlocal"], g["nghost"], g["neighs"])

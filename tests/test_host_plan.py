@@ -187,3 +187,24 @@ def test_two_rank_decomposition_over_gloo(shape, tmp_path):
         assert r[k]["slablo"][w0] == pytest.approx(lo) and r[k]["slabhi"][w0 + 1] == pytest.approx(hi)
         assert bool(r[k]["pbc_any"][w0]) == (r[k]["loc"][split] == 0)
         assert bool(r[k]["pbc_any"][w0 + 1]) == (r[k]["loc"][split] == 1)
+
+
+def test_lammps_data_file_setup(tmp_path):
+    """-f <data file> (ref/setup.cpp:215-301): atoms and velocities come from the file in id order, the bin
+    grid from the density (about 16 atoms per 2x2x2 bins); golden bins from the reference binary."""
+    from helpers import golden, lattice_for_datafile, write_lammps_data
+    g = golden("reference_datafile.json")["lj_data_half"]
+    x, v, prd = lattice_for_datafile()
+    data = write_lammps_data(str(tmp_path / "atoms.data"), x, v, prd)
+    s = Simulation.plan(["-i", input_file("in.lj.miniMD"), "-f", data])
+    assert s.geti("natoms") == len(x) == s.geti("nlocal")
+    assert [s.geti("nbinx"), s.geti("nbiny"), s.geti("nbinz")] == g["bins"]
+    assert np.array_equal(s.host_array("x").reshape(-1, 3), x) and np.array_equal(s.host_array("v").reshape(-1, 3), v)
+    assert s.getr("xprd") == prd[0]
+    # -b overrides the density rule; a deck that names the file on line 4 is equivalent to -f
+    assert Simulation.plan(["-i", input_file("in.lj.miniMD"), "-f", data, "-b", "3"]).geti("nbinx") == 3
+    deck = tmp_path / "in.data.miniMD"
+    deck.write_text(open(input_file("in.lj.miniMD")).read().replace("none ", data + " ", 1))
+    assert Simulation.plan(["-i", str(deck)]).geti("nlocal") == len(x)
+    with pytest.raises(HostError):
+        Simulation.plan(["-i", input_file("in.lj.miniMD"), "-f", str(tmp_path / "nope.data")])
