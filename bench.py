@@ -59,7 +59,7 @@ def box_cells(n_gpus: int, size: int):
 def workload_config(a, n_gpus):
     nx, ny, nz = box_cells(n_gpus, a.size)
     return {
-        "workload": f"in.lj.miniMD -s {a.size} per GPU ({nx}x{ny}x{nz} cells, {4 * nx * ny * nz} atoms), "
+        "workload": f"in.{a.force}.miniMD -s {a.size} per GPU ({nx}x{ny}x{nz} cells, {4 * nx * ny * nz} atoms), "
                     f"{'half' if a.half_neigh else 'full'} neighbor list, ghost_newton {a.ghost_newton if a.half_neigh else 0}, "
                     f"{'FP64' if a.precision == 'f64' else 'FP32'}",
         "natoms": 4 * nx * ny * nz, "cells": [nx, ny, nz], "half_neigh": a.half_neigh,
@@ -257,8 +257,13 @@ def own_arm(a, n_gpus, rank, local_rank):
 
     nx, ny, nz = box_cells(n_gpus, a.size)
     total_md = MD_STEPS_PER_STEP * (a.warmup + a.steps)
-    args = ["-i", input_file("in.lj.miniMD"), "-nx", nx, "-ny", ny, "-nz", nz, "-n", total_md, "--half_neigh", a.half_neigh,
-            "-gn", a.ghost_newton, "--quiet"]
+    args = ["-i", input_file("in.lj.miniMD" if a.force == "lj" else "in.eam.miniMD"), "-nx", nx, "-ny", ny, "-nz", nz, "-n", total_md,
+            "--half_neigh", a.half_neigh, "-gn", a.ghost_newton, "--quiet"]
+    if a.force == "eam":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from helpers import eam_file            # the Cu_u6 table: oracle/_ref copy or the committed fixture
+        args += ["--eam_file", eam_file()]
+        a.no_e2e = True                          # the e2e leg drives the LJ entry points
     sim = Simulation(args, a.precision, rank=rank, nranks=n_gpus, device=local_rank, nccl_id=nccl_id)
     ctx = sim.context()
     if a.tpa:
@@ -301,7 +306,9 @@ def own_arm(a, n_gpus, rank, local_rank):
     peak, peak_src = measured_peak()
     force_avg_ms = f_ms / max(f_calls, 1)
     achieved = force_bytes / (force_avg_ms * 1e-3) / 1e9 if force_avg_ms > 0 else 0.0
-    kern = f"force_lj_kernel<{'double' if s == 8 else 'float'},half={a.half_neigh},gn={a.ghost_newton if a.half_neigh else 0}>"
+    kern = f"force_{a.force}_kernel<{'double' if s == 8 else 'float'},half={a.half_neigh},gn={a.ghost_newton if a.half_neigh else 0}>"
+    if a.force == "eam":                                          # two passes over the rows + fp traffic
+        force_bytes = nlocal * (2 * ((4 * n_per_atom + 4) + (3 * s + 4)) + f_bytes + 2 * s)
     roofline = {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": profiled_traffic("force_lj_half_f64" if a.half_neigh else "force_lj_full_f64"),
                 "algorithmic_bytes_per_launch": force_bytes, "avg_launch_ms": force_avg_ms, "launches_timed": f_calls,
@@ -403,6 +410,7 @@ def main():
     ap.add_argument("--half_neigh", type=int, default=1)
     ap.add_argument("--ghost_newton", type=int, default=1)
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--force", default="lj", choices=["lj", "eam"], help="lj = the headline metric; eam = BASELINE.json config 4 (use --size 64)")
     ap.add_argument("--tpa", type=int, default=0, help="lanes per atom in the force kernel (0 = library default)")
     ap.add_argument("--no-e2e", dest="no_e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")

@@ -55,6 +55,37 @@ __global__ void final_integrate_kernel(Vec4<T>* __restrict__ v, const Vec4<T>* _
   }
 }
 
+// finalIntegrate of step n fused with initialIntegrate of step n+1 (they are adjacent in the time loop and
+// use the same force): one pass over x, v, f instead of two.  The two velocity half-kicks stay two
+// separate roundings, so the result is bit-identical to running the two kernels back to back.
+template <class T, int KE>
+__global__ void final_initial_integrate_kernel(Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ v,
+                                               const Vec4<T>* __restrict__ f, int nlocal, T dt, T dtforce, T mass,
+                                               double* __restrict__ ke) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double e = 0.0;
+  if (i < nlocal) {
+    Vec4<T> xi = x[i], vi = v[i];
+    const Vec4<T> fi = f[i];
+    vi.x += dtforce * fi.x;
+    vi.y += dtforce * fi.y;
+    vi.z += dtforce * fi.z;
+    if (KE) e = (double)((vi.x * vi.x + vi.y * vi.y + vi.z * vi.z) * mass);
+    vi.x += dtforce * fi.x;
+    vi.y += dtforce * fi.y;
+    vi.z += dtforce * fi.z;
+    xi.x += dt * vi.x;
+    xi.y += dt * vi.y;
+    xi.z += dt * vi.z;
+    x[i] = xi;
+    v[i] = vi;
+  }
+  if (KE) {
+    const double a[1] = {e};
+    block_accumulate<1>(a, ke);
+  }
+}
+
 template <class T>
 __global__ void sum_mv2_kernel(const Vec4<T>* __restrict__ v, int nlocal, T mass, double* __restrict__ out) {
   double e = 0.0;
@@ -174,6 +205,70 @@ __global__ void halo_unpack_f_kernel(Vec4<T>* __restrict__ f, const int* __restr
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   red_add3(f + list[k], buf[3 * k + 0], buf[3 * k + 1], buf[3 * k + 2]);
+}
+
+// both swaps of one dimension layer in one launch (they are independent: same source range, disjoint
+// ghost ranges), so a remote dimension costs pack -> ONE NCCL group (2 sends + 2 recvs) -> unpack.
+// Buffer layout: [3*count0 reals of swap 0 | 3*count1 reals of swap 1].
+template <class T>
+__global__ void halo_pack_x_pair_kernel(const Vec4<T>* __restrict__ x, SwapPairDev sp, T xprd, T yprd, T zprd,
+                                        T* __restrict__ buf) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  int k = g, s = 0;
+  if (k >= sp.count[0]) { k -= sp.count[0]; s = 1; }
+  if (k >= sp.count[s]) return;
+  Vec4<T> p = x[sp.list[s][k]];
+  if (sp.any[s]) {
+    p.x = p.x + sp.flag[s][0] * xprd;
+    p.y = p.y + sp.flag[s][1] * yprd;
+    p.z = p.z + sp.flag[s][2] * zprd;
+  }
+  buf[(size_t)3 * g + 0] = p.x;
+  buf[(size_t)3 * g + 1] = p.y;
+  buf[(size_t)3 * g + 2] = p.z;
+}
+template <class T, int ZERO_F>
+__global__ void halo_unpack_x_pair_kernel(Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, int first0, int n0, int first1,
+                                          int n1, const T* __restrict__ buf) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n0 + n1) return;
+  const int dst = g < n0 ? first0 + g : first1 + (g - n0);
+  Vec4<T> p = x[dst];  // keeps the type lane set by borders
+  p.x = buf[(size_t)3 * g + 0];
+  p.y = buf[(size_t)3 * g + 1];
+  p.z = buf[(size_t)3 * g + 2];
+  x[dst] = p;
+  if (ZERO_F) {
+    Vec4<T> z; z.x = z.y = z.z = z.w = (T)0;
+    f[dst] = z;
+  }
+}
+template <class T>
+__global__ void halo_pack_f_pair_kernel(const Vec4<T>* __restrict__ f, int first0, int n0, int first1, int n1,
+                                        T* __restrict__ buf) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n0 + n1) return;
+  const Vec4<T> v = f[g < n0 ? first0 + g : first1 + (g - n0)];
+  buf[(size_t)3 * g + 0] = v.x;
+  buf[(size_t)3 * g + 1] = v.y;
+  buf[(size_t)3 * g + 2] = v.z;
+}
+// buf: [3*count0 | 3*count1] force contributions for the atoms of send list 0 / 1
+template <class T>
+__global__ void halo_unpack_f_pair_kernel(Vec4<T>* __restrict__ f, SwapPairDev sp, const T* __restrict__ buf) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  int k = g, s = 0;
+  if (k >= sp.count[0]) { k -= sp.count[0]; s = 1; }
+  if (k >= sp.count[s]) return;
+  red_add3(f + sp.list[s][k], buf[(size_t)3 * g + 0], buf[(size_t)3 * g + 1], buf[(size_t)3 * g + 2]);
+}
+template <class T>
+__global__ void gather_scalar_pair_kernel(const T* __restrict__ a, SwapPairDev sp, T* __restrict__ buf) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  int k = g, s = 0;
+  if (k >= sp.count[0]) { k -= sp.count[0]; s = 1; }
+  if (k >= sp.count[s]) return;
+  buf[g] = a[sp.list[s][k]];
 }
 
 // scalar per-atom forward halo (EAM fp, ForceEAM::communicate ref/force_eam.cpp:851-914)

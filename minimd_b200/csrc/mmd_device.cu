@@ -177,6 +177,7 @@ struct mmd_ctx {
 
   // per-phase device timing of mmd_run (option "phase_timing"): marks[k] closes an interval of phase
   // mark_phase[k]; intervals are summed after the loop's final synchronisation.
+  bool fuse_integrate = true;  // mmd_run: finalIntegrate(n) + initialIntegrate(n+1) in one kernel
   bool phase_timing = false;
   std::vector<cudaEvent_t> marks;
   std::vector<int> mark_phase;
@@ -626,6 +627,16 @@ template <class T> struct Impl {
     }
     return MMD_OK;
   }
+  static int final_initial(mmd_ctx* c, double dt, double dtforce, bool ke, double mass) {
+    const int g = div_up(c->nlocal, TPB);
+    if (ke) {
+      CU(cudaMemsetAsync(c->d_ev + 2, 0, sizeof(double), c->stream));
+      LAUNCH(c, (final_initial_integrate_kernel<T, 1>), g, TPB, c->x.as<V>(), c->v.as<V>(), c->f.as<V>(), c->nlocal, (T)dt, (T)dtforce, (T)mass, c->d_ev + 2);
+    } else {
+      LAUNCH(c, (final_initial_integrate_kernel<T, 0>), g, TPB, c->x.as<V>(), c->v.as<V>(), c->f.as<V>(), c->nlocal, (T)dt, (T)dtforce, (T)mass, c->d_ev + 2);
+    }
+    return MMD_OK;
+  }
   static int sum_mv2(mmd_ctx* c, double mass, double* out) {
     CU(cudaMemsetAsync(c->d_ev + 2, 0, sizeof(double), c->stream));
     const int g = std::max(1, std::min(div_up(c->nlocal, TPB), 148 * 8));
@@ -665,6 +676,22 @@ template <class T> struct Impl {
     NC(ncclGroupEnd());
     return MMD_OK;
   }
+  // both swaps of a dimension layer in ONE group: 2 sends + 2 receives, buffers [part 0 | part 1]
+  static int sendrecv_pair2(mmd_ctx* c, const T* sbuf, size_t s0, size_t s1, int dst0, int dst1, T* r0, T* r1, size_t n0,
+                            size_t n1, int src0, int src1) {
+    if (!c->nccl) return set_err(MMD_ERR_STATE, "remote swap requested but mmd_comm_nccl_init was not called");
+    NC(ncclGroupStart());
+    if (s0) NC(ncclSend(sbuf, s0, nccl_real(), dst0, c->nccl, c->stream));
+    if (n0) NC(ncclRecv(r0, n0, nccl_real(), src0, c->nccl, c->stream));
+    if (s1) NC(ncclSend(sbuf + s0, s1, nccl_real(), dst1, c->nccl, c->stream));
+    if (n1) NC(ncclRecv(r1, n1, nccl_real(), src1, c->nccl, c->stream));
+    NC(ncclGroupEnd());
+    return MMD_OK;
+  }
+  static int sendrecv_pair(mmd_ctx* c, const T* sbuf, size_t s0, size_t s1, int dst0, int dst1, T* rbuf, size_t n0, size_t n1,
+                           int src0, int src1) {
+    return sendrecv_pair2(c, sbuf, s0, s1, dst0, dst1, rbuf, rbuf + n0, n0, n1, src0, src1);
+  }
 #endif
 
   static int communicate(mmd_ctx* c, bool zero_ghost_f) {
@@ -679,19 +706,16 @@ template <class T> struct Impl {
         else LAUNCH(c, (halo_forward_self_kernel<T, 0>), div_up(n, TPB), TPB, c->x.as<V>(), c->f.as<V>(), sp, px, py, pz);
       } else {
 #ifdef MMD_WITH_NCCL
-        for (int s = 0; s < nsw; s++) {
-          const int ww = w + s;
-          const int ns = c->sw[ww].sendnum, nr = c->sw[ww].recvnum;
-          MM(c->sendbuf.reserve((size_t)3 * ns * sizeof(T), c->stream, 0, 1.5));
-          MM(c->recvbuf.reserve((size_t)3 * nr * sizeof(T), c->stream, 0, 1.5));
-          LAUNCH(c, halo_pack_x_kernel<T>, div_up(ns, TPB), TPB, c->x.as<V>(), c->sw[ww].list.as<int>(), ns,
-                 c->swaps.pbc_any[ww], c->swaps.pbc_flagx[ww], c->swaps.pbc_flagy[ww], c->swaps.pbc_flagz[ww], px, py, pz,
-                 c->sendbuf.as<T>());
-          MM(sendrecv(c, c->sendbuf.p, (size_t)3 * ns, c->swaps.sendproc[ww], c->recvbuf.p, (size_t)3 * nr,
-                      c->swaps.recvproc[ww], nccl_real()));
-          if (zero_ghost_f) LAUNCH(c, (halo_unpack_x_kernel<T, 1>), div_up(nr, TPB), TPB, c->x.as<V>(), c->f.as<V>(), c->sw[ww].firstrecv, nr, c->recvbuf.as<T>());
-          else LAUNCH(c, (halo_unpack_x_kernel<T, 0>), div_up(nr, TPB), TPB, c->x.as<V>(), c->f.as<V>(), c->sw[ww].firstrecv, nr, c->recvbuf.as<T>());
-        }
+        if (nsw != 2) return set_err(MMD_ERR_STATE, "communicate: odd swap count");
+        const SwapPairDev sp = pair_desc(c, w, 2);
+        const int ns0 = c->sw[w].sendnum, ns1 = c->sw[w + 1].sendnum, nr0 = c->sw[w].recvnum, nr1 = c->sw[w + 1].recvnum;
+        MM(c->sendbuf.reserve((size_t)3 * (ns0 + ns1) * sizeof(T), c->stream, 0, 1.5));
+        MM(c->recvbuf.reserve((size_t)3 * (nr0 + nr1) * sizeof(T), c->stream, 0, 1.5));
+        LAUNCH(c, halo_pack_x_pair_kernel<T>, div_up(ns0 + ns1, TPB), TPB, c->x.as<V>(), sp, px, py, pz, c->sendbuf.as<T>());
+        MM(sendrecv_pair(c, c->sendbuf.as<T>(), (size_t)3 * ns0, (size_t)3 * ns1, c->swaps.sendproc[w], c->swaps.sendproc[w + 1],
+                         c->recvbuf.as<T>(), (size_t)3 * nr0, (size_t)3 * nr1, c->swaps.recvproc[w], c->swaps.recvproc[w + 1]));
+        if (zero_ghost_f) LAUNCH(c, (halo_unpack_x_pair_kernel<T, 1>), div_up(nr0 + nr1, TPB), TPB, c->x.as<V>(), c->f.as<V>(), c->sw[w].firstrecv, nr0, c->sw[w + 1].firstrecv, nr1, c->recvbuf.as<T>());
+        else LAUNCH(c, (halo_unpack_x_pair_kernel<T, 0>), div_up(nr0 + nr1, TPB), TPB, c->x.as<V>(), c->f.as<V>(), c->sw[w].firstrecv, nr0, c->sw[w + 1].firstrecv, nr1, c->recvbuf.as<T>());
 #else
         return set_err(MMD_ERR_STATE, "remote swap but library built without NCCL");
 #endif
@@ -711,16 +735,17 @@ template <class T> struct Impl {
         LAUNCH(c, halo_reverse_self_kernel<T>, div_up(sp.count[0] + sp.count[1], TPB), TPB, c->f.as<V>(), sp);
       } else {
 #ifdef MMD_WITH_NCCL
-        for (int s = nsw - 1; s >= 0; s--) {
-          const int ww = w + s;
-          const int ns = c->sw[ww].sendnum, nr = c->sw[ww].recvnum;
-          MM(c->sendbuf.reserve((size_t)3 * nr * sizeof(T), c->stream, 0, 1.5));
-          MM(c->recvbuf.reserve((size_t)3 * ns * sizeof(T), c->stream, 0, 1.5));
-          LAUNCH(c, halo_pack_f_kernel<T>, div_up(nr, TPB), TPB, c->f.as<V>(), c->sw[ww].firstrecv, nr, c->sendbuf.as<T>());
-          MM(sendrecv(c, c->sendbuf.p, (size_t)3 * nr, c->swaps.recvproc[ww], c->recvbuf.p, (size_t)3 * ns,
-                      c->swaps.sendproc[ww], nccl_real()));
-          LAUNCH(c, halo_unpack_f_kernel<T>, div_up(ns, TPB), TPB, c->f.as<V>(), c->sw[ww].list.as<int>(), ns, c->recvbuf.as<T>());
-        }
+        if (nsw != 2) return set_err(MMD_ERR_STATE, "reverse_communicate: odd swap count");
+        const SwapPairDev sp = pair_desc(c, w, 2);
+        const int ns0 = c->sw[w].sendnum, ns1 = c->sw[w + 1].sendnum, nr0 = c->sw[w].recvnum, nr1 = c->sw[w + 1].recvnum;
+        MM(c->sendbuf.reserve((size_t)3 * (nr0 + nr1) * sizeof(T), c->stream, 0, 1.5));
+        MM(c->recvbuf.reserve((size_t)3 * (ns0 + ns1) * sizeof(T), c->stream, 0, 1.5));
+        LAUNCH(c, halo_pack_f_pair_kernel<T>, div_up(nr0 + nr1, TPB), TPB, c->f.as<V>(), c->sw[w].firstrecv, nr0,
+               c->sw[w + 1].firstrecv, nr1, c->sendbuf.as<T>());
+        // ghost forces travel back along the swap: to the rank the ghosts came from, from the rank mine went to
+        MM(sendrecv_pair(c, c->sendbuf.as<T>(), (size_t)3 * nr0, (size_t)3 * nr1, c->swaps.recvproc[w], c->swaps.recvproc[w + 1],
+                         c->recvbuf.as<T>(), (size_t)3 * ns0, (size_t)3 * ns1, c->swaps.sendproc[w], c->swaps.sendproc[w + 1]));
+        LAUNCH(c, halo_unpack_f_pair_kernel<T>, div_up(ns0 + ns1, TPB), TPB, c->f.as<V>(), sp, c->recvbuf.as<T>());
 #else
         return set_err(MMD_ERR_STATE, "remote swap but library built without NCCL");
 #endif
@@ -739,14 +764,15 @@ template <class T> struct Impl {
         LAUNCH(c, halo_forward_scalar_self_kernel<T>, div_up(sp.count[0] + sp.count[1], TPB), TPB, a, sp);
       } else {
 #ifdef MMD_WITH_NCCL
-        for (int s = 0; s < nsw; s++) {
-          const int ww = w + s;
-          const int ns = c->sw[ww].sendnum, nr = c->sw[ww].recvnum;
-          MM(c->sendbuf.reserve((size_t)ns * sizeof(T), c->stream, 0, 1.5));
-          LAUNCH(c, gather_scalar_kernel<T>, div_up(ns, TPB), TPB, a, c->sw[ww].list.as<int>(), ns, c->sendbuf.as<T>());
-          MM(sendrecv(c, c->sendbuf.p, (size_t)ns, c->swaps.sendproc[ww], a + c->sw[ww].firstrecv, (size_t)nr,
-                      c->swaps.recvproc[ww], nccl_real()));
-        }
+        if (nsw != 2) return set_err(MMD_ERR_STATE, "forward_scalar: odd swap count");
+        const SwapPairDev sp = pair_desc(c, w, 2);
+        const int ns0 = c->sw[w].sendnum, ns1 = c->sw[w + 1].sendnum, nr0 = c->sw[w].recvnum, nr1 = c->sw[w + 1].recvnum;
+        MM(c->sendbuf.reserve((size_t)(ns0 + ns1) * sizeof(T), c->stream, 0, 1.5));
+        LAUNCH(c, gather_scalar_pair_kernel<T>, div_up(ns0 + ns1, TPB), TPB, a, sp, c->sendbuf.as<T>());
+        // ghosts of one swap are contiguous from firstrecv: receive straight into the array
+        MM(sendrecv_pair2(c, c->sendbuf.as<T>(), (size_t)ns0, (size_t)ns1, c->swaps.sendproc[w], c->swaps.sendproc[w + 1],
+                          a + c->sw[w].firstrecv, a + c->sw[w + 1].firstrecv, (size_t)nr0, (size_t)nr1, c->swaps.recvproc[w],
+                          c->swaps.recvproc[w + 1]));
 #else
         return set_err(MMD_ERR_STATE, "remote swap but library built without NCCL");
 #endif
@@ -847,9 +873,13 @@ template <class T> struct Impl {
     const bool reverse_needed = p->halfneigh && p->ghost_newton;
     if (elapsed_ms) CU(cudaEventRecord(c->ev0, c->stream));
     MM(phase_mark(c, -1));
+    const int last = p->first_step + p->ntimes - 1;
     for (int n = p->first_step; n < p->first_step + p->ntimes; n++) {
-      MM(initial(c, p->dt, p->dtforce, false));
-      MM(phase_mark(c, MMD_PHASE_INTEGRATE));
+      // (from the second step on, initialIntegrate already ran fused with the previous finalIntegrate)
+      if (n == p->first_step || !c->fuse_integrate) {
+        MM(initial(c, p->dt, p->dtforce, false));
+        MM(phase_mark(c, MMD_PHASE_INTEGRATE));
+      }
       if ((n + 1) % p->neigh_every) {
         MM(communicate(c, false));
         MM(phase_mark(c, MMD_PHASE_COMM));
@@ -873,7 +903,8 @@ template <class T> struct Impl {
         MM(reverse(c));
         MM(phase_mark(c, MMD_PHASE_COMM));
       }
-      MM(final_(c, p->dtforce, ev != 0, p->mass));
+      if (n < last && c->fuse_integrate) MM(final_initial(c, p->dt, p->dtforce, ev != 0, p->mass));
+      else MM(final_(c, p->dtforce, ev != 0, p->mass));
       MM(phase_mark(c, MMD_PHASE_INTEGRATE));
       if (ev) {
         MM(read_ev(c, 4));
@@ -1483,6 +1514,8 @@ int mmd_set_option(mmd_ctx* c, const char* key, long long value) {
   } else if (k == "eam_threads_per_atom") {
     if (!pow2(value)) return set_err(MMD_ERR_ARG, "eam_threads_per_atom must be 1,2,4,8,16 or 32");
     c->eam_tpa = (int)value;
+  } else if (k == "fuse_integrate") {
+    c->fuse_integrate = value != 0;
   } else if (k == "phase_timing") {
     c->phase_timing = value != 0;
   } else if (k == "force_nonuniform") {  // testing: exercise the per-type table path

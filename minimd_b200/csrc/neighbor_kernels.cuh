@@ -128,6 +128,7 @@ __global__ void permute_atoms_kernel(const int* __restrict__ order, int n, const
 // MODE 2: half list, no ghost_newton (every bin: skip j<i; own bin: skip j==i)
 constexpr int NB_WARPS = 8;       // warps (= bins) per block
 constexpr int NB_CHUNK = 32;      // local atoms of one bin handled per sweep
+constexpr int NB_MAXC = 768;      // candidate ids staged per warp and pass (a typical stencil holds 290 / 570)
 
 template <class T, int MODE>
 __global__ void __launch_bounds__(NB_WARPS * 32)
@@ -138,6 +139,10 @@ neigh_build_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* __restr
                    unsigned long long* __restrict__ total, int maxneighs) {
   __shared__ Vec4<T> s_xi[NB_WARPS][NB_CHUNK];
   __shared__ int s_id[NB_WARPS][NB_CHUNK];
+  // The stencil's candidates arrive as ~13 (half) / ~25 (full) short runs of consecutive bins; testing them run by
+  // run leaves most 32-lane sweeps half empty.  Their ids are first packed, in stencil order, into this
+  // per-warp buffer (bit 31 marks candidates of the warp's own bin), then swept 32 at a time.
+  __shared__ unsigned s_cand[NB_WARPS][NB_MAXC];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int b = blockIdx.x * NB_WARPS + w;
   if (b >= mbins) return;
@@ -159,24 +164,42 @@ neigh_build_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* __restr
     __syncwarp();
     int my_n = 0;  // row length of i-atom `lane`
 
-    for (int r = 0; r < nruns; r++) {
-      const int2 run = runs[r];
-      int blo = b + run.x, bhi = blo + run.y;
-      blo = max(blo, 0);
-      bhi = min(bhi, mbins);
-      if (bhi <= blo) continue;
-      const int c_begin = bin_start[blo], c_end = bin_start[bhi];
-      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+    int r = 0, off = 0;  // next run / offset inside it still to be staged
+    while (r < nruns) {
+      // ---- pack candidate ids of as many runs as fit ----
+      int filled = 0;
+      while (r < nruns && filled < NB_MAXC) {
+        const int2 run = runs[r];
+        int blo = b + run.x, bhi = blo + run.y;
+        blo = max(blo, 0);
+        bhi = min(bhi, mbins);
+        if (bhi <= blo) { r++; off = 0; continue; }
+        const int c_begin = bin_start[blo] + off, c_end = bin_start[bhi];
+        const int take = min(c_end - c_begin, NB_MAXC - filled);
+        for (int k = lane; k < take; k += 32) {
+          const int c = c_begin + k;
+          const unsigned own = (c >= s0 && c < s1) ? 0x80000000u : 0u;
+          s_cand[w][filled + k] = (unsigned)bin_atoms[c] | own;
+        }
+        filled += take;
+        if (c_begin + take == c_end) { r++; off = 0; }
+        else off += take;  // buffer full in the middle of a run: continue it in the next pass
+      }
+      __syncwarp();
+      // ---- sweep the packed candidates, 32 per iteration ----
+      for (int c0 = 0; c0 < filled; c0 += 32) {
         const int c = c0 + lane;
-        const bool valid = c < c_end;
+        const bool valid = c < filled;
         int j = 0;
+        bool own_bin = false;
         Vec4<T> xj;
         xj.x = xj.y = xj.z = xj.w = (T)0;
         if (valid) {
-          j = bin_atoms[c];
+          const unsigned e = s_cand[w][c];
+          own_bin = (e & 0x80000000u) != 0u;
+          j = (int)(e & 0x7fffffffu);
           xj = x[j];
         }
-        const bool own_bin = (c >= s0) && (c < s1);
         const int tj = lane_to_type(xj.w);
         for (int t = 0; t < nloc; t++) {
           const Vec4<T> xi = s_xi[w][t];
@@ -208,6 +231,7 @@ neigh_build_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* __restr
           if (lane == t) my_n += __popc(m);
         }
       }
+      __syncwarp();
     }
     if (is_local) numneigh[my_id] = my_n;
     int mx = is_local ? my_n : 0;
