@@ -268,6 +268,7 @@ def own_arm(a, n_gpus, rank, local_rank):
     ctx = sim.context()
     if a.tpa:
         ctx.set_option("lj_threads_per_atom", a.tpa)
+    ctx.set_option("tile_lists", a.tile)      # effective from the next neighbor build (inside the warm-up)
     natoms = sim.geti("natoms")
     stream = torch.cuda.ExternalStream(ctx.stream)
 
@@ -306,11 +307,15 @@ def own_arm(a, n_gpus, rank, local_rank):
     peak, peak_src = measured_peak()
     force_avg_ms = f_ms / max(f_calls, 1)
     achieved = force_bytes / (force_avg_ms * 1e-3) / 1e9 if force_avg_ms > 0 else 0.0
-    kern = f"force_{a.force}_kernel<{'double' if s == 8 else 'float'},half={a.half_neigh},gn={a.ghost_newton if a.half_neigh else 0}>"
+    tiled = bool(ctx.query("list_tile"))
+    kern = (f"force_{a.force}_{'tile_' if tiled else ''}kernel<{'double' if s == 8 else 'float'},half={a.half_neigh},"
+            f"gn={a.ghost_newton if a.half_neigh else 0}>")
     if a.force == "eam":                                          # two passes over the rows + fp traffic
         force_bytes = nlocal * (2 * ((4 * n_per_atom + 4) + (3 * s + 4)) + f_bytes + 2 * s)
     roofline = {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": profiled_traffic("force_lj_half_f64" if a.half_neigh else "force_lj_full_f64"),
+                "frac": achieved / peak,
+                "traffic": profiled_traffic("force_lj_tile_f64" if tiled else ("force_lj_half_f64" if a.half_neigh else "force_lj_full_f64")),
+                "list_format": "tile-resident 16-bit rows, owner-computes" if tiled else "classic rows of global ids",
                 "algorithmic_bytes_per_launch": force_bytes, "avg_launch_ms": force_avg_ms, "launches_timed": f_calls,
                 "neighbors_per_atom": n_per_atom, "peak_source": peak_src,
                 "share_of_step": f_ms / max(sum(v[0] for v in phases.values()), 1e-12)}
@@ -412,6 +417,8 @@ def main():
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--force", default="lj", choices=["lj", "eam"], help="lj = the headline metric; eam = BASELINE.json config 4 (use --size 64)")
     ap.add_argument("--tpa", type=int, default=0, help="lanes per atom in the force kernel (0 = library default)")
+    ap.add_argument("--tile", type=int, default=1, help="1: tile-resident neighbor lists + shared-memory force kernel (default); "
+                                                        "0: classic rows of global ids (gather / scatter kernels)")
     ap.add_argument("--no-e2e", dest="no_e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     a = ap.parse_args()

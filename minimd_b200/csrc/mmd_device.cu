@@ -17,6 +17,7 @@
 #include "integrate_comm_kernels.cuh"
 #include "neighbor_kernels.cuh"
 #include "scan.cuh"
+#include "tile_kernels.cuh"
 
 #ifdef MMD_WITH_NCCL
 #include <nccl.h>
@@ -60,6 +61,16 @@ static inline int launch_impl(int line, C* ctx, K kern, int grid, int block, Arg
   return MMD_OK;
 }
 #define LAUNCH(ctx, kern, grid, block, ...) MM(launch_impl(__LINE__, ctx, kern, grid, block, __VA_ARGS__))
+template <class C, class K, class... Args>
+static inline int launch_smem_impl(int line, C* ctx, K kern, int grid, int block, size_t smem, Args... args) {
+  if (grid <= 0) return MMD_OK;
+  kern<<<grid, block, smem, ctx->stream>>>(args...);
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return launch_fail(line, e);
+  return MMD_OK;
+}
+#define LAUNCH_SMEM(ctx, kern, grid, block, smem, ...) MM(launch_smem_impl(__LINE__, ctx, kern, grid, block, smem, __VA_ARGS__))
 
 #ifdef MMD_WITH_NCCL
 #define NC(call)                                                                                  \
@@ -138,6 +149,18 @@ struct mmd_ctx {
   int neigh_builds = 0, neigh_resizes = 0;
   int list_half = -1, list_gn = -1;
 
+  // tile-resident lists (tile_kernels.cuh): 16-bit tile-local rows + shared-memory force kernels
+  bool tile_enable = true;  // option "tile_lists"
+  bool tile_ok = false;     // bin grid / stencil admit the tiling (decided by mmd_neigh_setup)
+  bool list_tile = false;   // format of the current list
+  TileGeo tgeo;
+  int nsruns = 0;           // runs of the symmetric (full) stencil
+  DevBuf sruns, tile_runs, tile_center, tile_info, tile_slots, trows, tnum;
+  int tcap = 0;             // row capacity (16-bit entries, multiple of 8)
+  int tcap_floor = 0;       // raised when a build overflowed its rows
+  int tile_max_h = 0, tile_max_full = 0;
+  int tile_builds = 0, tile_fallbacks = 0;
+
   // Force
   bool have_lj = false, lj_uniform = true;
   DevBuf lj_cut, lj_s6, lj_eps;
@@ -164,7 +187,8 @@ struct mmd_ctx {
   int nranks = 1, rank = 0;
 
   // device scalars + pinned mirror
-  // d_scal ints : [0] status, [1] max_n, [2] max_bin, [3] border total 0, [4] border total 1, [5] scan total
+  // d_scal ints : [0] status, [1] max_n, [2] max_bin, [3] border total 0, [4] border total 1, [5] scan total,
+  //               [6..9] exchange/border counts, [10] max full row, [11] max halo window, [12] tile status
   // d_ev doubles: [0] eng, [1] virial, [2] sum m v^2, [3] embed energy
   int* d_scal = nullptr;
   unsigned long long* d_total = nullptr;
@@ -407,6 +431,7 @@ template <class T> struct Impl {
 
   static int read_status(mmd_ctx* c) {  // status + running max bin occupancy
     CU(cudaMemcpyAsync(c->h_scal, c->d_scal, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_scal + 10, c->d_scal + 10, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->max_bin_seen = std::max(c->max_bin_seen, c->h_scal[2]);
     if (c->h_scal[0] & 1) return set_err(MMD_ERR_STATE, "atom outside the bin grid (lost atom / bad coordinates)");
@@ -423,11 +448,129 @@ template <class T> struct Impl {
   }
 
   // ---- neighbor build ------------------------------------------------------------------
+  static bool want_tile(mmd_ctx* c) { return c->tile_enable && c->tile_ok && !c->have_eam; }
+
+  // tile-resident build (tile_kernels.cuh).  *done = false when the tiling does not fit this state (halo window
+  // larger than the shared-memory capacity, stencil leaving the grid): the caller builds classic rows instead.
+  static int build_tile(mmd_ctx* c, int halfneigh, int gn, bool* done) {
+    *done = false;
+    const int nall = c->nlocal + c->nghost;
+    TileGeo& g = c->tgeo;
+    // tile origin: the first bin that can own a local atom opens a tile (no half-empty tiles along the low faces)
+    {
+      const double binv[3] = {c->geo.bininvx, c->geo.bininvy, c->geo.bininvz};
+      const int mlo[3] = {c->geo.mbinxlo, c->geo.mbinylo, c->geo.mbinzlo};
+      const int tb[3] = {TBX, TBY, TBZ};
+      int o[3];
+      for (int d = 0; d < 3; d++) {
+        const int first = std::max(0, (int)(c->lo[d] * binv[d]) - mlo[d]);
+        o[d] = (tb[d] - first % tb[d]) % tb[d];
+      }
+      g.ox = o[0]; g.oy = o[1]; g.oz = o[2];
+      g.ntx = (g.mbx + g.ox + TBX - 1) / TBX; g.nty = (g.mby + g.oy + TBY - 1) / TBY; g.ntz = (g.mbz + g.oz + TBZ - 1) / TBZ;
+      g.ntiles = g.ntx * g.nty * g.ntz;
+    }
+    MM(c->tile_runs.reserve((size_t)g.ntiles * g.nrun * sizeof(int2), c->stream));
+    MM(c->tile_center.reserve((size_t)g.ntiles * TILE_NCENTER * sizeof(int4), c->stream));
+    MM(c->tile_info.reserve((size_t)g.ntiles * sizeof(int2), c->stream));
+    MM(c->tile_slots.reserve((size_t)std::max(c->cap, nall) * sizeof(int), c->stream));
+    // one row per binned atom, numbered tile by tile (the rows of ghost atoms are never touched)
+    MM(c->tnum.reserve((size_t)std::max(nall, 1) * sizeof(int2), c->stream, 0, 1.1));
+    CU(cudaMemsetAsync(c->tnum.p, 0xff, (size_t)std::max(nall, 1) * sizeof(int2), c->stream));
+    CU(cudaMemsetAsync(c->d_scal + 10, 0, 4 * sizeof(int), c->stream));
+    LAUNCH(c, tile_table_kernel, div_up(g.ntiles, 4), 128, g, c->bin_start.as<int>(), c->bin_atoms.as<int>(), c->mbins,
+           c->nlocal, c->tile_runs.as<int2>(), c->tile_center.as<int4>(), c->tile_info.as<int2>(), c->d_scal + 11,
+           c->d_scal + 13);
+    CU(cudaMemcpyAsync(c->tile_slots.p, c->bin_atoms.p, (size_t)nall * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    const int mode = halfneigh ? (gn ? 1 : 2) : 0;
+    for (;;) {
+      // row stride: twice the reference's maxneighs until a build has shown the longest full row, then that + 15 %
+      if (c->tile_max_full > 0) c->tcap = std::max(c->tcap_floor, ((int)(c->tile_max_full * 1.15) + 8) & ~7);
+      else c->tcap = std::max(c->tcap_floor, (((halfneigh ? 2 : 1) * c->maxneighs) + 7) & ~7);
+      MM(c->trows.reserve((size_t)std::max(nall, 1) * c->tcap * sizeof(unsigned short), c->stream, 0, 1.05));
+      CU(cudaMemsetAsync(c->d_scal + 1, 0, sizeof(int), c->stream));
+      CU(cudaMemsetAsync(c->d_scal + 10, 0, sizeof(int), c->stream));
+      CU(cudaMemsetAsync(c->d_total, 0, sizeof(unsigned long long), c->stream));
+      const int grid = div_up(c->mbins, NB_WARPS);
+#define NBT_ARGS                                                                                                           \
+  c->x.as<V>(), c->nlocal, c->bin_start.as<int>(), c->bin_atoms.as<int>(), c->mbins, c->sruns.as<StencilRun>(), c->nsruns, \
+      c->cutneighsq.as<T>(), c->ntypes, g, c->tile_runs.as<int2>(), c->tile_center.as<int4>(),                             \
+      c->trows.as<unsigned short>(), c->tcap, c->numneigh.as<int>(), c->tnum.as<int2>(), c->d_scal + 12, c->d_scal + 1,    \
+      c->d_scal + 10, c->d_total
+      if (mode == 0) LAUNCH(c, (neigh_build_tile_kernel<T, 0>), grid, NB_WARPS * 32, NBT_ARGS);
+      if (mode == 1) LAUNCH(c, (neigh_build_tile_kernel<T, 1>), grid, NB_WARPS * 32, NBT_ARGS);
+      if (mode == 2) LAUNCH(c, (neigh_build_tile_kernel<T, 2>), grid, NB_WARPS * 32, NBT_ARGS);
+#undef NBT_ARGS
+      CU(cudaMemcpyAsync(c->h_total, c->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+      MM(read_status(c));
+      c->tile_max_h = c->h_scal[11];
+      // shared-memory capacity: positions (+ one type byte per atom on the per-type parameter path) of the largest
+      // halo window must fit the 227 KB a CTA can own; up to ~4600 atoms (FP64) two CTAs share an SM
+      const int hcap_limit = (int)((227 * 1024 - 4096) / (3 * sizeof(T) + 1)) & ~63;
+      if (c->h_scal[12] != 0 || c->tile_max_h > hcap_limit) {
+        c->tile_fallbacks++;
+        return MMD_OK;  // *done stays false
+      }
+      g.hcap = std::max(64, (c->tile_max_h + 63) & ~63);
+      const int max_half = c->h_scal[1], max_full = c->h_scal[10];
+      bool again = false;
+      if (max_half >= c->maxneighs) {  // ref/neighbor.cpp:186-208, on the reference's own row lengths
+        c->maxneighs = (int)(max_half * 1.2);
+        c->neigh_resizes++;
+        again = true;
+      }
+      if (max_full > c->tcap) {
+        c->tcap_floor = ((int)(max_full * 1.2) + 7) & ~7;
+        again = true;
+      }
+      c->tile_max_full = std::max(c->tile_max_full, max_full);
+      if (!again) break;
+    }
+    c->neigh_stride = (c->maxneighs + 7) & ~7;
+    c->list_tile = true;
+    c->tile_builds++;
+    *done = true;
+    return MMD_OK;
+  }
+
+  // reference-format rows (global ids, half subset for half lists) of a tile-resident list, into c->neighbors
+  static int export_rows(mmd_ctx* c) {
+    if (!c->list_tile) return MMD_OK;
+    const TileGeo& g = c->tgeo;
+    MM(c->neighbors.reserve((size_t)std::max(c->nlocal, 1) * c->neigh_stride * sizeof(int), c->stream, 0, 1.05));
+    LAUNCH(c, tile_rows_export_kernel, g.ntiles, TILE_THREADS, g, c->tile_runs.as<int2>(), c->tile_center.as<int4>(),
+           c->tile_info.as<int2>(), c->tile_slots.as<int>(), c->trows.as<unsigned short>(), c->tnum.as<int2>(), c->tcap,
+           c->nlocal, c->list_half ? 1 : 0, c->neighbors.as<int>(), c->neigh_stride, c->neigh_stride);
+    return MMD_OK;
+  }
+  // switch the current list to the classic format (kernels without a tile variant)
+  static int ensure_classic(mmd_ctx* c) {
+    if (!c->list_tile) return MMD_OK;
+    MM(export_rows(c));
+    c->list_tile = false;
+    return MMD_OK;
+  }
+
   static int build(mmd_ctx* c, int halfneigh, int gn, int* maxneighs_io, long long* total_out) {
     if (maxneighs_io && *maxneighs_io > 0) c->maxneighs = *maxneighs_io;
     const int nall = c->nlocal + c->nghost;
     MM(binatoms_async(c, nall));
     MM(c->numneigh.reserve((size_t)std::max(c->nlocal, 1) * sizeof(int), c->stream, 0, 1.1));
+    c->list_tile = false;
+    if (want_tile(c)) {
+      bool done = false;
+      MM(build_tile(c, halfneigh, gn, &done));
+      if (done) {
+        c->total_neigh = (long long)*c->h_total;
+        c->neigh_rows = c->nlocal;
+        c->neigh_builds++;
+        c->list_half = halfneigh;
+        c->list_gn = gn;
+        if (maxneighs_io) *maxneighs_io = c->maxneighs;
+        if (total_out) *total_out = c->total_neigh;
+        return MMD_OK;
+      }
+    }
     const int mode = halfneigh ? (gn ? 1 : 2) : 0;
     for (;;) {
       c->neigh_stride = (c->maxneighs + 7) & ~7;
@@ -486,10 +629,42 @@ template <class T> struct Impl {
     }
     return ev ? lj_launch<TPA, 0, 0, 1>(c) : lj_launch<TPA, 0, 0, 0>(c);
   }
+  // tile-resident list: owner-computes shared-memory kernel (tile_kernels.cuh)
+  template <int EV, int UNI> static int lj_tile_launch(mmd_ctx* c, int half) {
+    LJTileParams<T> P;
+    P.cutforcesq = (T)c->lj_cut0; P.sigma6 = (T)c->lj_s60; P.epsilon = (T)c->lj_eps0;
+    P.cutforcesq_tab = c->lj_cut.as<T>(); P.sigma6_tab = c->lj_s6.as<T>(); P.epsilon_tab = c->lj_eps.as<T>();
+    P.ntypes = c->ntypes;
+    // every pair is visited from both ends: half-list semantics sum each pair once (ref/force_lj.cpp:246-248),
+    // full-list semantics report twice the pair energy and half the double-counted virial (:441-442)
+    P.e_scale = half ? 0.5 : 1.0;
+    P.v_scale = 0.5;
+    const TileGeo& g = c->tgeo;
+    const size_t smem = tile_smem_bytes<T>(g.hcap, !UNI);
+    static bool attr_done = false;
+    if (!attr_done) {
+      CU(cudaFuncSetAttribute(force_lj_tile_kernel<T, EV, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+      attr_done = true;
+    }
+    LAUNCH_SMEM(c, (force_lj_tile_kernel<T, EV, UNI>), g.ntiles, TILE_THREADS, smem, c->x.as<V>(), c->f.as<V>(), g,
+                c->tile_runs.as<int2>(), c->tile_center.as<int4>(), c->tile_info.as<int2>(), c->tile_slots.as<int>(),
+                c->trows.as<unsigned short>(), c->tnum.as<int2>(), c->tcap, c->nlocal, P, c->d_ev);
+    return MMD_OK;
+  }
+
   // clear_f: zero f[0,nall) first (half lists; skipped by mmd_run when a fused prologue did it)
   static int lj_async(mmd_ctx* c, int half, int gn, int ev, bool clear_f) {
     if (!c->have_lj) return set_err(MMD_ERR_STATE, "force_lj: mmd_force_lj_setup missing");
     if (c->neigh_rows != c->nlocal) return set_err(MMD_ERR_STATE, "force_lj: neighbor list is stale (build first)");
+    if (c->list_tile) {
+      if ((half != 0) != (c->list_half != 0)) return set_err(MMD_ERR_STATE, "force_lj: list was built for the other neighbor style");
+      // ghosts receive no force in this scheme; keep their f at zero so that a following reverse halo is a no-op
+      if (half && clear_f && c->nghost > 0)
+        CU(cudaMemsetAsync(c->f.as<V>() + c->nlocal, 0, (size_t)c->nghost * sizeof(V), c->stream));
+      if (ev) CU(cudaMemsetAsync(c->d_ev, 0, 2 * sizeof(double), c->stream));
+      if (c->lj_uniform) return ev ? lj_tile_launch<1, 1>(c, half) : lj_tile_launch<0, 1>(c, half);
+      return ev ? lj_tile_launch<1, 0>(c, half) : lj_tile_launch<0, 0>(c, half);
+    }
     if (half && clear_f) CU(cudaMemsetAsync(c->f.p, 0, (size_t)(c->nlocal + c->nghost) * sizeof(V), c->stream));
     if (ev) CU(cudaMemsetAsync(c->d_ev, 0, 2 * sizeof(double), c->stream));
     switch (c->lj_tpa ? c->lj_tpa : (half ? 2 : 4)) {
@@ -592,6 +767,7 @@ template <class T> struct Impl {
     return ev ? eam_launch<TPA, 1, 0>(c, half) : eam_launch<TPA, 0, 0>(c, half);
   }
   static int eam_async(mmd_ctx* c, int half, int ev) {
+    MM(ensure_classic(c));
     if (!c->have_eam) return set_err(MMD_ERR_STATE, "force_eam: mmd_force_eam_setup missing");
     if (c->neigh_rows != c->nlocal) return set_err(MMD_ERR_STATE, "force_eam: neighbor list is stale (build first)");
     MM(c->rho.reserve((size_t)c->cap * sizeof(T), c->stream));
@@ -896,10 +1072,11 @@ template <class T> struct Impl {
         MM(phase_mark(c, MMD_PHASE_NEIGH));
       }
       const int ev = p->thermo_nstat > 0 ? ((n + 1) % p->thermo_nstat == 0) : 0;
-      if (p->force_style == 0) MM(lj_async(c, p->halfneigh, p->ghost_newton, ev, true));
+      // tile-resident lists: every atom's force is complete after the kernel -- nothing to clear, nothing to send back
+      if (p->force_style == 0) MM(lj_async(c, p->halfneigh, p->ghost_newton, ev, !c->list_tile));
       else MM(eam_async(c, p->halfneigh, ev));
       MM(phase_mark(c, MMD_PHASE_FORCE));
-      if (reverse_needed) {
+      if (reverse_needed && !c->list_tile) {
         MM(reverse(c));
         MM(phase_mark(c, MMD_PHASE_COMM));
       }
@@ -1100,7 +1277,8 @@ int mmd_ctx_destroy(mmd_ctx* c) {
                     &c->tile_sums, &c->numneigh, &c->neighbors, &c->lj_cut, &c->lj_s6, &c->lj_eps, &c->eam_rho_val,
                     &c->eam_rho_der, &c->eam_z2_val, &c->eam_z2_der, &c->eam_frho_val, &c->eam_frho_der, &c->eam_cut,
                     &c->rho, &c->fp, &c->border_tiles, &c->sendbuf, &c->recvbuf, &c->exch_flag, &c->exch_pos,
-                    &c->exch_holes};
+                    &c->exch_holes, &c->sruns, &c->tile_runs, &c->tile_center, &c->tile_info, &c->tile_slots, &c->trows,
+                    &c->tnum};
   for (DevBuf* b : bufs) b->release();
   for (int w = 0; w < MMD_MAX_SWAPS; w++) c->sw[w].list.release();
 #ifdef MMD_WITH_NCCL
@@ -1193,6 +1371,48 @@ int mmd_neigh_setup(mmd_ctx* c, const mmd_bin_geometry* g, const int* stencil, i
   MM(c->cursor.reserve((size_t)(mb + 1) * sizeof(int), c->stream));
   c->have_geo = true;
   c->neigh_rows = -1;
+  c->list_tile = false;
+  // ---- tile-resident lists: symmetric closure of the stencil (a half stencil holds only the "upper" bins,
+  // ref/neighbor.cpp:424-440), decoded into (dz,dy,dx) and merged into runs along x.  Linear offsets order
+  // exactly like the reference's (k,j,i) loops because |dx| < mbinx/2 and |dy| < mbiny/2.
+  c->tile_ok = false;
+  {
+    std::vector<int> full(stencil, stencil + nstencil);
+    for (int k = 0; k < nstencil; k++) full.push_back(-stencil[k]);
+    std::sort(full.begin(), full.end());
+    full.erase(std::unique(full.begin(), full.end()), full.end());
+    const int mx = g->mbinx, my = g->mbiny;
+    auto rnd_div = [](int a, int b) { return (a >= 0 ? a + b / 2 : a - b / 2) / b; };
+    int sx = 0, sy = 0, sz = 0;
+    bool ok = true;
+    std::vector<StencilRun> sr;
+    for (int o : full) {
+      const int dz = rnd_div(o, mx * my);
+      const int rem = o - dz * mx * my;
+      const int dy = rnd_div(rem, mx);
+      const int dx = rem - dy * mx;
+      if (2 * std::abs(dx) >= mx || 2 * std::abs(dy) >= my) ok = false;
+      sx = std::max(sx, std::abs(dx)); sy = std::max(sy, std::abs(dy)); sz = std::max(sz, std::abs(dz));
+      if (!sr.empty() && sr.back().off + sr.back().len == o && sr.back().dy == dy && sr.back().dz == dz) sr.back().len++;
+      else sr.push_back(StencilRun{o, 1, dy, dz});
+    }
+    TileGeo t;
+    t.mbx = g->mbinx; t.mby = g->mbiny; t.mbz = g->mbinz;
+    t.ox = t.oy = t.oz = 0;  // origin and tile counts are fixed at build time (they depend on the sub-box)
+    t.ntx = (t.mbx + TBX - 1) / TBX; t.nty = (t.mby + TBY - 1) / TBY; t.ntz = (t.mbz + TBZ - 1) / TBZ;
+    t.sx = sx; t.sy = sy; t.sz = sz;
+    t.nry = TBY + 2 * sy; t.nrz = TBZ + 2 * sz; t.nrun = t.nry * t.nrz;
+    t.ntiles = t.ntx * t.nty * t.ntz;
+    t.hcap = 0;  // sized at every build from the largest halo window
+    if (t.nrun > TILE_MAXRUN) ok = false;
+    if (ok) {
+      MM(c->sruns.reserve(sr.size() * sizeof(StencilRun), c->stream));
+      CU(cudaMemcpy(c->sruns.p, sr.data(), sr.size() * sizeof(StencilRun), cudaMemcpyHostToDevice));
+      c->nsruns = (int)sr.size();
+      c->tgeo = t;
+      c->tile_ok = true;
+    }
+  }
   return MMD_OK;
 }
 
@@ -1226,6 +1446,7 @@ int mmd_neigh_download(mmd_ctx* c, int* numneigh, int* neighbors, int nrows, int
   if (numneigh) CU(cudaMemcpyAsync(numneigh, c->numneigh.p, (size_t)nrows * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   if (neighbors) {
     if (maxneighs < 1) return set_err(MMD_ERR_ARG, "neigh_download: maxneighs");
+    MM(DISPATCH(c, Impl<double>::export_rows(c), Impl<float>::export_rows(c)));
     const int ncopy = std::min(maxneighs, c->maxneighs);
     MM(c->stage_i.reserve((size_t)nrows * maxneighs * sizeof(int), c->stream));
     CU(cudaMemsetAsync(c->stage_i.p, 0xff, (size_t)nrows * maxneighs * sizeof(int), c->stream));
@@ -1243,6 +1464,7 @@ int mmd_neigh_upload(mmd_ctx* c, const int* numneigh, const int* neighbors, int 
   if (!numneigh || !neighbors || nrows != c->nlocal || maxneighs < 1) return set_err(MMD_ERR_ARG, "neigh_upload: bad arguments (nrows must equal nlocal)");
   c->maxneighs = maxneighs;
   c->neigh_stride = (maxneighs + 7) & ~7;
+  c->list_tile = false;
   MM(c->numneigh.reserve((size_t)std::max(nrows, 1) * sizeof(int), c->stream));
   MM(c->neighbors.reserve((size_t)std::max(nrows, 1) * c->neigh_stride * sizeof(int), c->stream));
   MM(c->stage_i.reserve((size_t)nrows * maxneighs * sizeof(int), c->stream));
@@ -1500,6 +1722,15 @@ int mmd_query_int(mmd_ctx* c, const char* key, long long* value) {
   else if (k == "exchange_sent") *value = c->exch_sent;
   else if (k == "exchange_received") *value = c->exch_received;
   else if (k == "nranks") *value = c->nranks;
+  else if (k == "tile_lists") *value = c->tile_enable;
+  else if (k == "list_tile") *value = c->list_tile;
+  else if (k == "tile_ok") *value = c->tile_ok;
+  else if (k == "tile_builds") *value = c->tile_builds;
+  else if (k == "tile_fallbacks") *value = c->tile_fallbacks;
+  else if (k == "tile_row_capacity") *value = c->tcap;
+  else if (k == "tile_max_halo") *value = c->tile_max_h;
+  else if (k == "tile_max_full") *value = c->tile_max_full;
+  else if (k == "tile_count") *value = c->tile_ok ? c->tgeo.ntiles : 0;
   else return set_err(MMD_ERR_ARG, "query: unknown key '%s'", key);
   return MMD_OK;
 }
@@ -1514,6 +1745,8 @@ int mmd_set_option(mmd_ctx* c, const char* key, long long value) {
   } else if (k == "eam_threads_per_atom") {
     if (!pow2(value)) return set_err(MMD_ERR_ARG, "eam_threads_per_atom must be 1,2,4,8,16 or 32");
     c->eam_tpa = (int)value;
+  } else if (k == "tile_lists") {  // 1: tile-resident lists + shared-memory force kernels where they apply; 0: classic rows
+    c->tile_enable = value != 0;  // takes effect at the next neighbor build
   } else if (k == "fuse_integrate") {
     c->fuse_integrate = value != 0;
   } else if (k == "phase_timing") {

@@ -51,12 +51,15 @@ CASES = [
 # ------------------------------------------------------------------------------------------
 # binning / borders / neighbor build / sort : bit-exact
 # ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tile", [1, 0])
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 @pytest.mark.parametrize("steps", [0, 40])
 @pytest.mark.parametrize("case", range(len(CASES)))
-def test_borders_bins_and_lists_are_bit_exact(case, steps, prec):
+def test_borders_bins_and_lists_are_bit_exact(case, steps, prec, tile):
+    """tile=1: tile-resident 16-bit rows exported back to the reference's format; tile=0: classic rows."""
     o = melted(CASES[case], steps, prec)
     c = context_from_oracle(o)
+    c.set_option("tile_lists", tile)
     c.exchange()
     c.borders()
     # ghosts: counts, send lists, positions (+- prd shifts) and types
@@ -81,6 +84,7 @@ def test_borders_bins_and_lists_are_bit_exact(case, steps, prec):
     # neighbor lists
     half, gn = o.geti("halfneigh"), o.geti("ghost_newton")
     mxn, total = c.build(half, gn, 100)
+    assert c.query("list_tile") == tile
     num, nb = c.neigh_download()
     onum, onb = o.numneigh(), o.neighbors()
     assert mxn == o.geti("maxneighs")
@@ -90,9 +94,11 @@ def test_borders_bins_and_lists_are_bit_exact(case, steps, prec):
         assert np.array_equal(nb[i, :num[i]], onb[i, :num[i]]), f"row {i}"
 
 
-def test_neighbor_resize_protocol_matches_reference():
+@pytest.mark.parametrize("tile", [1, 0])
+def test_neighbor_resize_protocol_matches_reference(tile):
     o = Oracle(Config(nx=6, ny=6, nz=6, halfneigh=0), "f64")
     c = context_from_oracle(o)
+    c.set_option("tile_lists", tile)
     c.exchange()
     c.borders()
     o.seti("maxneighs", 20)
@@ -145,8 +151,9 @@ def test_coord2bin_edge_cases_bit_exact():
 # ------------------------------------------------------------------------------------------
 # forces
 # ------------------------------------------------------------------------------------------
-def setup_lists(o):
+def setup_lists(o, tile=1):
     c = context_from_oracle(o)
+    c.set_option("tile_lists", tile)
     c.exchange()
     c.borders()
     c.build(o.geti("halfneigh"), o.geti("ghost_newton"), 100)
@@ -154,11 +161,38 @@ def setup_lists(o):
 
 
 @pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("half,gn", [(1, 1), (1, 0), (0, 0)])
+@pytest.mark.parametrize("size", [(8, 8, 8), (5, 7, 9)])
+def test_lj_tile_force_energy_virial(half, gn, size, prec):
+    """Tile-resident lists: every local atom's force is complete after the kernel (no scatter, no reverse
+    halo), so half+ghost_newton is compared with the oracle AFTER its reverse_communicate."""
+    o = melted(dict(nx=size[0], ny=size[1], nz=size[2], halfneigh=half, ghost_newton=gn), 40, prec)
+    c = setup_lists(o, tile=1)
+    assert c.query("list_tile") == 1
+    o.seti("evflag", 1)
+    o.call("force_compute")
+    if half and gn:
+        o.call("reverse_communicate")
+    eng, vir = c.lj_compute(half, gn, 1)
+    nl = o.nlocal
+    f = c.download("f", count=nl)["f"]
+    assert_close(f, o.f(nl), ktol(prec), "f")
+    etol = 1e-11 if prec == "f64" else 2e-3
+    assert abs(eng - o.getr("eng_vdwl")) <= etol * abs(o.getr("eng_vdwl"))
+    assert abs(vir - o.getr("virial")) <= etol * max(abs(o.getr("virial")), abs(o.getr("eng_vdwl")))
+    # a reverse halo after the kernel must be a no-op (ghost forces are kept at zero)
+    c.reverse_communicate()
+    assert np.array_equal(c.download("f", count=nl)["f"], f)
+    c.lj_compute(half, gn, 0)
+    assert_close(c.download("f", count=nl)["f"], f, 1e-13 if prec == "f64" else 1e-5, "f(ev=0) vs f(ev=1)")
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
 @pytest.mark.parametrize("tpa", [1, 4, 8, 32])
 @pytest.mark.parametrize("half,gn", [(1, 1), (1, 0), (0, 0)])
 def test_lj_force_energy_virial(half, gn, tpa, prec):
     o = melted(dict(nx=8, ny=8, nz=8, halfneigh=half, ghost_newton=gn), 40, prec)
-    c = setup_lists(o)
+    c = setup_lists(o, tile=0)
     c.set_option("lj_threads_per_atom", tpa)
     o.seti("evflag", 1)
     o.call("force_compute")
@@ -176,7 +210,8 @@ def test_lj_force_energy_virial(half, gn, tpa, prec):
     assert_close(f0, f, 1e-13 if prec == "f64" else 1e-5, "f(ev=0) vs f(ev=1)")
 
 
-def test_lj_per_type_tables_path():
+@pytest.mark.parametrize("tile", [1, 0])
+def test_lj_per_type_tables_path(tile):
     """Distinct epsilon/sigma per type pair exercises the non-uniform table kernels."""
     o = melted(dict(nx=6, ny=6, nz=6, halfneigh=0, ghost_newton=0, ntypes=3), 20, "f64")
     nn = 9
@@ -186,7 +221,8 @@ def test_lj_per_type_tables_path():
     eps[:] = sym(rng.uniform(0.8, 1.2, (3, 3))).ravel()
     s6[:] = sym(rng.uniform(0.9, 1.1, (3, 3))).ravel()
     cut[:] = sym(rng.uniform(5.0, 6.25, (3, 3))).ravel()
-    c = setup_lists(o)
+    c = setup_lists(o, tile)
+    assert c.query("list_tile") == tile
     assert c.query("lj_uniform") == 0
     o.seti("evflag", 1)
     o.call("force_compute")
@@ -220,10 +256,11 @@ def test_eam_force_energy_virial(half, uniform, prec):
 # ------------------------------------------------------------------------------------------
 # integrate / halo / thermo
 # ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tile", [1, 0])
 @pytest.mark.parametrize("prec", ["f64", "f32"])
-def test_integrate_pbc_halo_and_thermo_kernels(prec):
+def test_integrate_pbc_halo_and_thermo_kernels(prec, tile):
     o = melted(dict(nx=8, ny=8, nz=8), 40, prec)
-    c = setup_lists(o)
+    c = setup_lists(o, tile)
     nl, na = o.nlocal, o.nall
     tol = 1e-14 if prec == "f64" else 1e-6
     # forces first (both sides), then reverse halo
@@ -281,16 +318,22 @@ RUN_CASES = [
 ]
 
 
+@pytest.mark.parametrize("tile", [1, 0])
 @pytest.mark.parametrize("force,half,gn,prec,tol", RUN_CASES)
-def test_time_loop_matches_oracle(force, half, gn, prec, tol):
+def test_time_loop_matches_oracle(force, half, gn, prec, tol, tile):
+    if tile and force == "eam":
+        pytest.skip("EAM runs on classic rows")
     cfg = Config(nx=8, ny=8, nz=8, ntimes=100, force=force, halfneigh=half, ghost_newton=gn, thermo_nstat=10)
     o64 = Oracle(cfg, "f64")          # FP32 runs are judged against the FP64 oracle
     o = Oracle(cfg, prec)
     c = context_from_oracle(o)
+    c.set_option("tile_lists", tile)
     c.exchange()
     c.borders()
     c.build(o.geti("halfneigh"), o.geti("ghost_newton"), 100)
+    assert c.query("list_tile") == (tile if force == "lj" else 0)
     samples, ms = c.run(run_params(o, 100))
+    assert c.query("list_tile") == (tile if force == "lj" else 0)
     got = thermo_from_samples(o, samples)
     o64.run(100)
     st, T, U, P = o64.thermo_log()
