@@ -135,6 +135,7 @@ struct mmd_ctx {
   mmd_bin_geometry geo;
   int mbins = 0;
   std::vector<int> stencil;
+  std::vector<double> h_cutneighsq;
   int nruns = 0;
   DevBuf runs, cutneighsq;
   DevBuf atom_bin, bin_atoms, bincount, bin_start, cursor;
@@ -152,6 +153,7 @@ struct mmd_ctx {
   // tile-resident lists (tile_kernels.cuh): 16-bit tile-local rows + shared-memory force kernels
   bool tile_enable = true;  // option "tile_lists"
   bool tile_ok = false;     // bin grid / stencil admit the tiling (decided by mmd_neigh_setup)
+  bool tile_build2 = true;  // option "tile_build2": CTA-per-tile build from shared memory (0: warp-per-bin build)
   bool list_tile = false;   // format of the current list
   TileGeo tgeo;
   int nsruns = 0;           // runs of the symmetric (full) stencil
@@ -483,6 +485,29 @@ template <class T> struct Impl {
            c->d_scal + 13);
     CU(cudaMemcpyAsync(c->tile_slots.p, c->bin_atoms.p, (size_t)nall * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
     const int mode = halfneigh ? (gn ? 1 : 2) : 0;
+    // the largest halo window sizes the shared memory of the build and force kernels
+    MM(read_status(c));
+    c->tile_max_h = c->h_scal[11];
+    const int hcap_limit = (int)((227 * 1024 - 4096) / (3 * sizeof(T) + 1)) & ~63;
+    if (c->tile_max_h > hcap_limit) {
+      c->tile_fallbacks++;
+      return MMD_OK;  // *done stays false
+    }
+    g.hcap = std::max(64, (c->tile_max_h + 1 + 63) & ~63);  // + 1: the build's sentinel slot
+    Build2Params<T> B;
+    {
+      const std::vector<double>& cuts = c->h_cutneighsq;  // host copy kept by mmd_neigh_setup (values exact in T)
+      B.cut0 = (T)cuts[0];
+      B.uniform_cut = 1;
+      double cmax = cuts[0];
+      for (double v : cuts) { if (v != cuts[0]) B.uniform_cut = 0; cmax = std::max(cmax, v); }
+      B.band = (float)(1e-4 * cmax);
+      B.binsize[0] = 1.0 / c->geo.bininvx; B.binsize[1] = 1.0 / c->geo.bininvy; B.binsize[2] = 1.0 / c->geo.bininvz;
+      B.mbinlo[0] = c->geo.mbinxlo; B.mbinlo[1] = c->geo.mbinylo; B.mbinlo[2] = c->geo.mbinzlo;
+    }
+    const size_t b2_smem = build2_smem_bytes<T>(g, g.hcap, !B.uniform_cut);
+    const bool use_b2 = c->tile_build2 && c->nsruns <= TB2_MAXSR && b2_smem <= (size_t)(227 * 1024 - 2048) &&
+                        c->tile_max_h <= TB2_MAXH;
     for (;;) {
       // row stride: twice the reference's maxneighs until a build has shown the longest full row, then that + 15 %
       if (c->tile_max_full > 0) c->tcap = std::max(c->tcap_floor, ((int)(c->tile_max_full * 1.15) + 8) & ~7);
@@ -497,21 +522,45 @@ template <class T> struct Impl {
       c->cutneighsq.as<T>(), c->ntypes, g, c->tile_runs.as<int2>(), c->tile_center.as<int4>(),                             \
       c->trows.as<unsigned short>(), c->tcap, c->numneigh.as<int>(), c->tnum.as<int2>(), c->d_scal + 12, c->d_scal + 1,    \
       c->d_scal + 10, c->d_total
-      if (mode == 0) LAUNCH(c, (neigh_build_tile_kernel<T, 0>), grid, NB_WARPS * 32, NBT_ARGS);
-      if (mode == 1) LAUNCH(c, (neigh_build_tile_kernel<T, 1>), grid, NB_WARPS * 32, NBT_ARGS);
-      if (mode == 2) LAUNCH(c, (neigh_build_tile_kernel<T, 2>), grid, NB_WARPS * 32, NBT_ARGS);
+#define NB2_ARGS                                                                                                          \
+  c->x.as<V>(), c->nlocal, c->bin_start.as<int>(), c->bin_atoms.as<int>(), c->mbins, c->sruns.as<StencilRun>(), c->nsruns, \
+      c->cutneighsq.as<T>(), c->ntypes, g, B, c->tile_runs.as<int2>(), c->tile_center.as<int4>(), c->tile_info.as<int2>(),  \
+      c->trows.as<unsigned short>(), c->tcap, c->numneigh.as<int>(), c->tnum.as<int2>(), c->d_scal + 12, c->d_scal + 1,    \
+      c->d_scal + 10, c->d_total
+      if (use_b2) {
+        static bool attr_done = false;
+        const int smax = 227 * 1024 - 2048;
+        if (!attr_done) {
+          CU(cudaFuncSetAttribute(neigh_build_tile2_kernel<T, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+          CU(cudaFuncSetAttribute(neigh_build_tile2_kernel<T, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+          CU(cudaFuncSetAttribute(neigh_build_tile2_kernel<T, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+          CU(cudaFuncSetAttribute(neigh_build_tile2_kernel<T, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+          CU(cudaFuncSetAttribute(neigh_build_tile2_kernel<T, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+          CU(cudaFuncSetAttribute(neigh_build_tile2_kernel<T, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+          attr_done = true;
+        }
+        if (B.uniform_cut) {
+          if (mode == 0) LAUNCH_SMEM(c, (neigh_build_tile2_kernel<T, 0, 1>), g.ntiles, TB2_THREADS, b2_smem, NB2_ARGS);
+          if (mode == 1) LAUNCH_SMEM(c, (neigh_build_tile2_kernel<T, 1, 1>), g.ntiles, TB2_THREADS, b2_smem, NB2_ARGS);
+          if (mode == 2) LAUNCH_SMEM(c, (neigh_build_tile2_kernel<T, 2, 1>), g.ntiles, TB2_THREADS, b2_smem, NB2_ARGS);
+        } else {
+          if (mode == 0) LAUNCH_SMEM(c, (neigh_build_tile2_kernel<T, 0, 0>), g.ntiles, TB2_THREADS, b2_smem, NB2_ARGS);
+          if (mode == 1) LAUNCH_SMEM(c, (neigh_build_tile2_kernel<T, 1, 0>), g.ntiles, TB2_THREADS, b2_smem, NB2_ARGS);
+          if (mode == 2) LAUNCH_SMEM(c, (neigh_build_tile2_kernel<T, 2, 0>), g.ntiles, TB2_THREADS, b2_smem, NB2_ARGS);
+        }
+      } else {
+        if (mode == 0) LAUNCH(c, (neigh_build_tile_kernel<T, 0>), grid, NB_WARPS * 32, NBT_ARGS);
+        if (mode == 1) LAUNCH(c, (neigh_build_tile_kernel<T, 1>), grid, NB_WARPS * 32, NBT_ARGS);
+        if (mode == 2) LAUNCH(c, (neigh_build_tile_kernel<T, 2>), grid, NB_WARPS * 32, NBT_ARGS);
+      }
+#undef NB2_ARGS
 #undef NBT_ARGS
       CU(cudaMemcpyAsync(c->h_total, c->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
       MM(read_status(c));
-      c->tile_max_h = c->h_scal[11];
-      // shared-memory capacity: positions (+ one type byte per atom on the per-type parameter path) of the largest
-      // halo window must fit the 227 KB a CTA can own; up to ~4600 atoms (FP64) two CTAs share an SM
-      const int hcap_limit = (int)((227 * 1024 - 4096) / (3 * sizeof(T) + 1)) & ~63;
-      if (c->h_scal[12] != 0 || c->tile_max_h > hcap_limit) {
+      if (c->h_scal[12] != 0) {  // a stencil range left the bin grid: no tile mapping for this state
         c->tile_fallbacks++;
         return MMD_OK;  // *done stays false
       }
-      g.hcap = std::max(64, (c->tile_max_h + 63) & ~63);
       const int max_half = c->h_scal[1], max_full = c->h_scal[10];
       bool again = false;
       if (max_half >= c->maxneighs) {  // ref/neighbor.cpp:186-208, on the reference's own row lengths
@@ -1366,6 +1415,9 @@ int mmd_neigh_setup(mmd_ctx* c, const mmd_bin_geometry* g, const int* stencil, i
   const size_t nn = (size_t)c->ntypes * c->ntypes * c->prec;
   MM(c->cutneighsq.reserve(nn, c->stream));
   CU(cudaMemcpy(c->cutneighsq.p, cutneighsq, nn, cudaMemcpyHostToDevice));
+  c->h_cutneighsq.resize((size_t)c->ntypes * c->ntypes);
+  for (size_t k = 0; k < c->h_cutneighsq.size(); k++)
+    c->h_cutneighsq[k] = c->prec == 8 ? ((const double*)cutneighsq)[k] : (double)((const float*)cutneighsq)[k];
   MM(c->bincount.reserve((size_t)(mb + 1) * sizeof(int), c->stream));
   MM(c->bin_start.reserve((size_t)(mb + 1) * sizeof(int), c->stream));
   MM(c->cursor.reserve((size_t)(mb + 1) * sizeof(int), c->stream));
@@ -1747,6 +1799,8 @@ int mmd_set_option(mmd_ctx* c, const char* key, long long value) {
     c->eam_tpa = (int)value;
   } else if (k == "tile_lists") {  // 1: tile-resident lists + shared-memory force kernels where they apply; 0: classic rows
     c->tile_enable = value != 0;  // takes effect at the next neighbor build
+  } else if (k == "tile_build2") {
+    c->tile_build2 = value != 0;
   } else if (k == "fuse_integrate") {
     c->fuse_integrate = value != 0;
   } else if (k == "phase_timing") {

@@ -293,6 +293,351 @@ neigh_build_tile_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* __
 }
 
 // ---------------------------------------------------------------------------------------
+// Neighbor build, tile-resident version: one CTA per tile, one warp per centre pencil.
+//
+// The halo window is staged into shared memory as FP32 coordinates -- for an FP64 build relative to the window
+// origin, so their error is <= 2^-24 * window extent -- together with the tile-local start index of every bin of the
+// window.  The candidates of a bin are then ~25 contiguous ranges of tile-local indices, flattened once per bin into
+// a per-warp table; for every local atom of the bin the warp sweeps that table 32 candidates at a time (conflict-
+// free shared-memory reads, the atom's own coordinates in registers, row length in a warp-uniform register).
+// FP64 build: the FP32 distance only decides candidates farther than `band` from cutneighsq (band = 1e-4 * cutneighsq,
+// > 20x the worst-case FP32 error).  A sweep that met a candidate inside the band is rolled back and
+// repeated by the general loop, which re-evaluates such candidates from the FP64 positions with unfused arithmetic --
+// so every accept/reject decision is exactly the reference's (rsq <= cutneighsq, ref/neighbor.cpp:165,179).
+// FP32 build: absolute coordinates, unfused FP32 arithmetic, exact.  The general loop also serves the cases that need
+// atom ids or FP64 coordinates: ghosts in the atom's own bin (MODE 1) and the j>i filter of MODE 2.
+// Row order, half-list flag and counters are those of neigh_build_tile_kernel.
+// ---------------------------------------------------------------------------------------
+constexpr int TB2_MAXSR = 64;    // stencil runs of the symmetric stencil (25 for the usual 5x5x5 stencil)
+constexpr int TB2_NC = 768;      // candidates per table block (a 5x5x5 stencil holds ~570)
+constexpr int TB2_MAXH = 8190;   // tile-local indices must fit 13 bits (+ sentinel)
+constexpr unsigned short TB2_OWN = 0x2000, TB2_UP = 0x4000;   // candidate class in bits 13-14 (0: lower stencil half)
+constexpr int TB2_THREADS = 256, TB2_WARPS = TB2_THREADS / 32;  // each warp takes two centre pencils
+
+template <class T> struct Build2Params {
+  T cut0;         // cutneighsq when all type pairs share it
+  float band;     // FP64 build: |rsq32 - cut| <= band -> exact FP64 test
+  double binsize[3];
+  int mbinlo[3];
+  int uniform_cut;
+};
+
+template <class T> __host__ __device__ inline size_t build2_smem_bytes(const TileGeo& g, int hcap, bool with_types) {
+  return (size_t)hcap * 3 * sizeof(float) + (with_types ? (size_t)hcap : 0) + (size_t)g.nrun * (TBX + 2 * g.sx + 1) * sizeof(int) +
+         (size_t)TB2_WARPS * TB2_MAXSR * 3 * sizeof(int) + (2 * TILE_MAXRUN + 1) * sizeof(int) +
+         (size_t)TB2_WARPS * TB2_NC * sizeof(unsigned short) + 64;
+}
+
+// rare paths of the build, kept out of line so that the hot loop carries no predicated FP64 code
+template <class T>
+__device__ __noinline__ bool build2_exact_within(const Vec4<T>* __restrict__ x, int id_i, int id_j, T cut) {
+  const Vec4<T> xi = x[id_i];
+  const Vec4<T> xj = x[id_j];
+  return rsq_unfused(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z) <= cut;
+}
+// ref/neighbor.cpp:154-157: a ghost in the atom's own bin is skipped when it lies lexicographically (z,y,x) below
+template <class T>
+__device__ __noinline__ bool build2_ghost_below(const Vec4<T>* __restrict__ x, int id_i, int id_j) {
+  const Vec4<T> xi = x[id_i];
+  const Vec4<T> xj = x[id_j];
+  return (xj.z < xi.z) || (xj.z == xi.z && xj.y < xi.y) || (xj.z == xi.z && xj.y == xi.y && xj.x < xi.x);
+}
+
+template <class T, int MODE, int UC>
+__global__ void __launch_bounds__(TB2_THREADS, 3)
+neigh_build_tile2_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* __restrict__ bin_start,
+                         const int* __restrict__ bin_atoms, int mbins, const StencilRun* __restrict__ sruns, int nsr,
+                         const T* __restrict__ cutneighsq, int ntypes, TileGeo g, Build2Params<T> B,
+                         const int2* __restrict__ tile_runs, const int4* __restrict__ tile_center,
+                         const int2* __restrict__ tile_info, unsigned short* __restrict__ rows, int tcap,
+                         int* __restrict__ numneigh_half, int2* __restrict__ row_atom, int* __restrict__ status,
+                         int* __restrict__ max_half, int* __restrict__ max_full, unsigned long long* __restrict__ total_half) {
+  extern __shared__ __align__(16) unsigned char b2_smem[];
+  const int t = blockIdx.x;
+  const int2 inf = tile_info[t];
+  if (inf.y == 0) return;
+  const int H = inf.x;
+  const int WX1 = TBX + 2 * g.sx + 1;
+  float* sx = reinterpret_cast<float*>(b2_smem);
+  float* sy = sx + g.hcap;
+  float* sz = sy + g.hcap;
+  int* s_binoff = reinterpret_cast<int*>(sz + g.hcap);           // [nrun][WX1] tile-local start index of each window bin
+  int* s_rstart = s_binoff + g.nrun * WX1;                        // [16][TB2_MAXSR] per warp: first index of a stencil range
+  int* s_rpref = s_rstart + TB2_WARPS * TB2_MAXSR;                // [warps][TB2_MAXSR] exclusive prefix of range lengths
+  int* s_rinfo = s_rpref + TB2_WARPS * TB2_MAXSR;                 // [warps][TB2_MAXSR] slot0 of the pencil | flags in bits 30,31
+  int* s_run_start = s_rinfo + TB2_WARPS * TB2_MAXSR;             // [nrun]
+  int* s_run_off = s_run_start + TILE_MAXRUN;                     // [nrun+1]
+  unsigned short* s_ctab = reinterpret_cast<unsigned short*>(s_run_off + TILE_MAXRUN + 1);  // [16][TB2_NC] candidate table
+  unsigned char* st = reinterpret_cast<unsigned char*>(s_ctab + TB2_WARPS * TB2_NC);       // [hcap] types
+
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int tx = t % g.ntx, ty = (t / g.ntx) % g.nty, tz = t / (g.ntx * g.nty);
+  const int bx0 = tx * TBX - g.ox, by0 = ty * TBY - g.oy, bz0 = tz * TBZ - g.oz;
+  const int xlo = max(0, bx0 - g.sx), xhi = min(g.mbx, bx0 + TBX + g.sx);
+  // window origin (only used to keep the FP32 images small; any point near the tile would do)
+  const T org_x = sizeof(T) == 8 ? (T)((bx0 - g.sx + B.mbinlo[0]) * B.binsize[0]) : (T)0;
+  const T org_y = sizeof(T) == 8 ? (T)((by0 - g.sy + B.mbinlo[1]) * B.binsize[1]) : (T)0;
+  const T org_z = sizeof(T) == 8 ? (T)((bz0 - g.sz + B.mbinlo[2]) * B.binsize[2]) : (T)0;
+
+  const int2* tr = tile_runs + (size_t)t * g.nrun;
+  for (int p = threadIdx.x; p < g.nrun; p += blockDim.x) {
+    const int2 r = tr[p];
+    s_run_start[p] = r.x;
+    s_run_off[p] = r.y;
+  }
+  if (threadIdx.x == 0) {
+    s_run_off[g.nrun] = H;
+    sx[H] = sy[H] = sz[H] = 1.0e18f;  // sentinel candidate: fails every distance test
+    if (!UC) st[H] = 0;
+  }
+  __syncthreads();
+  // bin offsets of the window
+  for (int e = threadIdx.x; e < g.nrun * WX1; e += blockDim.x) {
+    const int p = e / WX1, wx = e - p * WX1;
+    const int y = by0 - g.sy + p % g.nry, z = bz0 - g.sz + p / g.nry;
+    int v = s_run_off[p + 1];
+    if (y >= 0 && y < g.mby && z >= 0 && z < g.mbz && xlo + wx < xhi)
+      v = s_run_off[p] + (bin_start[min(tile_bin_id(g, xlo + wx, y, z), mbins)] - s_run_start[p]);
+    s_binoff[e] = v;
+  }
+  // FP32 images of the positions (+ types)
+  for (int p = w; p < g.nrun; p += nw) {
+    const int start = s_run_start[p], off = s_run_off[p], len = s_run_off[p + 1] - off;
+    for (int k = lane; k < len; k += 32) {
+      const int id = __ldg(bin_atoms + start + k);
+      const Vec4<T> v = ldg4(x + id);
+      sx[off + k] = (float)(v.x - org_x);
+      sy[off + k] = (float)(v.y - org_y);
+      sz[off + k] = (float)(v.z - org_z);
+      if (!UC) st[off + k] = (unsigned char)lane_to_type(v.w);
+    }
+  }
+  __syncthreads();
+
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int* rstart = s_rstart + w * TB2_MAXSR;
+  int* rpref = s_rpref + w * TB2_MAXSR;
+  int* rinfo = s_rinfo + w * TB2_MAXSR;
+  unsigned short* ctab = s_ctab + w * TB2_NC;
+  const float fcut0 = (float)B.cut0, band = B.band;
+  int warp_max_h = 0, warp_max_f = 0;
+  unsigned long long warp_total = 0ull;
+
+  for (int cr = w; cr < TILE_NCENTER; cr += nw) {
+    const int cy = cr % TBY, cz = cr / TBY;
+    const int by = by0 + cy, bz = bz0 + cz;
+    if (by < 0 || by >= g.mby || bz < 0 || bz >= g.mbz) continue;
+    const int4 ce = tile_center[(size_t)t * TILE_NCENTER + cr];
+    const int pc = (cy + g.sy) + (cz + g.sz) * g.nry;
+    const int slot0_c = s_run_start[pc] - s_run_off[pc];
+    for (int cx = 0; cx < TBX; cx++) {
+      const int bx = bx0 + cx;
+      if (bx < 0 || bx >= g.mbx) continue;
+      const int xw = bx - xlo;
+      const int own_lo = s_binoff[pc * WX1 + xw], own_hi = s_binoff[pc * WX1 + xw + 1];
+      if (own_hi == own_lo) continue;
+      // does the bin own local atoms?  (ids ascend inside a bin: locals first)
+      if (__ldg(bin_atoms + slot0_c + own_lo) >= nlocal) continue;
+
+      // ---- candidate ranges of this bin, in stencil order ----
+      int ncand = 0;
+      for (int r0 = 0; r0 < nsr; r0 += 32) {
+        const int r = r0 + lane;
+        int start = 0, len = 0, info = 0;
+        if (r < nsr) {
+          const StencilRun run = sruns[r];
+          const int dxlo = run.off - (run.dz * g.mby + run.dy) * g.mbx;
+          const int yy = by + run.dy, zz = bz + run.dz;
+          const int wlo = xw + dxlo, whi = wlo + run.len;
+          if (yy < 0 || yy >= g.mby || zz < 0 || zz >= g.mbz || wlo < 0 || xlo + whi > xhi) {
+            atomicOr(status, 2);
+          } else {
+            const int p = (cy + g.sy + run.dy) + (cz + g.sz + run.dz) * g.nry;
+            start = s_binoff[p * WX1 + wlo];
+            len = s_binoff[p * WX1 + whi] - start;
+            const bool upper = run.dz > 0 || (run.dz == 0 && run.dy > 0);
+            const bool ownp = run.dz == 0 && run.dy == 0;
+            info = ((s_run_start[p] - s_run_off[p]) & 0x3fffffff) | (upper ? 0x80000000 : 0) | (ownp ? 0x40000000 : 0);
+          }
+        }
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        if (r < nsr) {
+          rstart[r] = start;
+          rpref[r] = ncand + incl - len;
+          rinfo[r] = info;
+        }
+        ncand += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      __syncwarp();
+
+      // first tile-local index of the bin that is NOT a local atom (ids ascend inside a bin: ghosts come last)
+      int ghost_lo = own_hi;
+      for (int k0 = own_lo; k0 < own_hi; k0 += 32) {
+        const int k = k0 + lane;
+        const bool gh = k < own_hi && __ldg(bin_atoms + slot0_c + k) >= nlocal;
+        const unsigned mg = __ballot_sync(0xffffffffu, gh);
+        if (mg) { ghost_lo = k0 + __ffs(mg) - 1; break; }
+      }
+
+      // ---- local atoms of the bin, 32 at a time; lane tt keeps the row lengths of atom i0+tt ----
+      for (int i0 = own_lo; i0 < ghost_lo; i0 += 32) {
+        const int nloc = min(32, ghost_lo - i0);
+        const int q_i0 = ce.z + (i0 - ce.x);  // rows of consecutive atoms of a pencil are consecutive
+        int my_n = 0, my_h = 0;
+
+        for (int cb0 = 0; cb0 < ncand; cb0 += TB2_NC) {
+          const int nblk = min(TB2_NC, ncand - cb0);
+          const int nblk32 = (nblk + 31) & ~31;
+          // ---- flatten this block of candidates: tile-local index | own-bin bit | upper-stencil bit ----
+          bool slow_blk = (MODE == 2);
+          __syncwarp();
+          for (int k = lane; k < nblk32; k += 32) {
+            unsigned short e = (unsigned short)H;  // padding: the sentinel
+            if (k < nblk) {
+              const int n = cb0 + k;
+              int lo = 0, hi = nsr - 1;
+              while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (rpref[mid] <= n) lo = mid; else hi = mid - 1;
+              }
+              const int info = rinfo[lo];
+              const int lc = rstart[lo] + (n - rpref[lo]);
+              const bool own_bin = (info & 0x40000000) && lc >= own_lo && lc < own_hi;
+              const bool upper = (info & 0x80000000) != 0 || ((info & 0x40000000) && lc >= own_hi);
+              e = (unsigned short)(lc | (own_bin ? TB2_OWN : 0) | (upper ? TB2_UP : 0));
+              if (MODE == 1 && own_bin && lc >= ghost_lo) slow_blk = true;
+            }
+            ctab[k] = e;
+          }
+          slow_blk = __any_sync(0xffffffffu, slow_blk);
+          __syncwarp();
+
+          for (int tt = 0; tt < nloc; tt++) {
+            const int li = i0 + tt;
+            const float xi = sx[li], yi = sy[li], zi = sz[li];
+            const int ti = UC ? 0 : (int)st[li];
+            unsigned short* rowp = rows + (size_t)(q_i0 + tt) * tcap;
+            const int n_s = __shfl_sync(0xffffffffu, my_n, tt), h_s = __shfl_sync(0xffffffffu, my_h, tt);
+            int n_t = n_s, h_t = h_s;
+            bool redo = slow_blk;
+            if (!slow_blk) {
+              // ---- lean loop: FP32 decision, no ids.  key = index | class bits; with thr = li | OWN:
+              //      key == thr <=> the atom itself;  key > thr <=> upper stencil half, or own bin and j > i ----
+              bool closeany = false;
+              const int thr = li | TB2_OWN;
+              for (int k0 = 0; k0 < nblk32; k0 += 32) {
+                const int key = ctab[k0 + lane] & 0x7fff;
+                const int lc = key & 0x1fff;
+                const float dx = xi - sx[lc], dy = yi - sy[lc], dz = zi - sz[lc];
+                float fc = fcut0;
+                if (!UC) fc = (float)__ldg(&cutneighsq[ti * ntypes + (int)st[lc]]);
+                bool ok;
+                if (sizeof(T) == 4) {
+                  ok = rsq_unfused(dx, dy, dz) <= fc;
+                } else {
+                  const float d = (dx * dx + dy * dy + dz * dz) - fc;
+                  ok = d < -band;
+                  closeany = closeany || (fabsf(d) <= band);
+                }
+                ok = ok && key != thr;
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                const bool half = MODE == 1 ? key > thr : true;
+                const unsigned mh = MODE == 0 ? m : __ballot_sync(0xffffffffu, ok && half);
+                if (ok) {
+                  const int pos = n_t + __popc(m & lt_mask);
+                  if (pos < tcap) rowp[pos] = (unsigned short)(lc | ((MODE != 0 && half) ? TILE_HALF_BIT : 0));
+                }
+                n_t += __popc(m);
+                h_t += __popc(mh);
+              }
+              redo = sizeof(T) == 8 && __any_sync(0xffffffffu, closeany);
+            }
+            if (redo) {
+              // ---- general loop: same sweep with ids at hand (exact FP64 test inside the band, ghost and j>i filters) ----
+              n_t = n_s;
+              h_t = h_s;
+              for (int k0 = 0; k0 < nblk; k0 += 32) {
+                const int k = k0 + lane;
+                const bool valid = k < nblk;
+                const unsigned e = ctab[valid ? k : 0];
+                const int lc = e & 0x1fff;
+                int slot_j = 0;
+                {
+                  const int n = cb0 + (valid ? k : 0);
+                  int lo = 0, hi = nsr - 1;
+                  while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (rpref[mid] <= n) lo = mid; else hi = mid - 1;
+                  }
+                  slot_j = (rinfo[lo] << 2) >> 2;  // low 30 bits, sign-extended: CSR slot of tile-local index 0 of that pencil
+                }
+                const float dx = xi - sx[lc], dy = yi - sy[lc], dz = zi - sz[lc];
+                T cut = B.cut0;
+                if (!UC) cut = __ldg(&cutneighsq[ti * ntypes + (int)st[lc]]);
+                bool ok;
+                if (sizeof(T) == 4) {
+                  ok = rsq_unfused(dx, dy, dz) <= (float)cut;
+                } else {
+                  const float d = (dx * dx + dy * dy + dz * dz) - (float)cut;
+                  ok = d < -band;
+                  if (valid && fabsf(d) <= band && lc != li)
+                    ok = build2_exact_within<T>(x, __ldg(bin_atoms + slot0_c + li), __ldg(bin_atoms + slot_j + lc), cut);
+                }
+                ok = ok && valid && lc != li;
+                bool half = true;
+                if (MODE == 1) {
+                  half = (e & TB2_UP) || ((e & TB2_OWN) && lc > li);
+                  if (ok && half && (e & TB2_OWN) && lc >= ghost_lo)
+                    half = !build2_ghost_below<T>(x, __ldg(bin_atoms + slot0_c + li), __ldg(bin_atoms + slot0_c + lc));
+                }
+                if (MODE == 2) {
+                  half = false;
+                  if (ok) half = __ldg(bin_atoms + slot_j + lc) > __ldg(bin_atoms + slot0_c + li);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                const unsigned mh = MODE == 0 ? m : __ballot_sync(0xffffffffu, ok && half);
+                if (ok) {
+                  const int pos = n_t + __popc(m & lt_mask);
+                  if (pos < tcap) rowp[pos] = (unsigned short)(lc | ((MODE != 0 && half) ? TILE_HALF_BIT : 0));
+                }
+                n_t += __popc(m);
+                h_t += __popc(mh);
+              }
+            }
+            if (lane == tt) { my_n = n_t; my_h = h_t; }
+          }
+        }
+        if (lane < nloc) {
+          const int my_id = __ldg(bin_atoms + slot0_c + i0 + lane);
+          numneigh_half[my_id] = my_h;
+          row_atom[q_i0 + lane] = make_int2(my_id, my_n);
+          warp_max_h = max(warp_max_h, my_h);
+          warp_max_f = max(warp_max_f, my_n);
+          warp_total += (unsigned long long)my_h;
+        }
+      }
+      __syncwarp();
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    warp_max_h = max(warp_max_h, __shfl_xor_sync(0xffffffffu, warp_max_h, o));
+    warp_max_f = max(warp_max_f, __shfl_xor_sync(0xffffffffu, warp_max_f, o));
+    warp_total += __shfl_xor_sync(0xffffffffu, warp_total, o);
+  }
+  if (lane == 0) {
+    atomicMax(max_half, warp_max_h);
+    atomicMax(max_full, warp_max_f);
+    atomicAdd(total_half, warp_total);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Shared-memory image of a tile: run tables + SoA positions of the halo window.
 // ---------------------------------------------------------------------------------------
 template <class T> struct TileSmem {
