@@ -301,13 +301,18 @@ def own_arm(a, n_gpus, rank, local_rank):
     s = 8 if a.precision == "f64" else 4
     nlocal = sim.geti("nlocal")
     n_per_atom = sim.geti("total_neigh") / max(nlocal, 1)
+    tiled = bool(ctx.query("list_tile"))
     f_bytes = (3 * s + 6 * s) if a.half_neigh else 3 * s        # half: clear + read-modify-write; full: one store
     force_bytes = nlocal * ((4 * n_per_atom + 4) + (3 * s + 4) + f_bytes)
+    # tile-resident lists: the force launch of every step but the last of an mmd_run call also performs that step's
+    # finalIntegrate and the next step's initialIntegrate (15 s + 9 s bytes per atom)
+    fused_verlet = tiled and a.force == "lj" and bool(ctx.query("fuse_force"))
+    if fused_verlet:
+        force_bytes += nlocal * 24 * s * (MD_STEPS_PER_STEP - 1) / MD_STEPS_PER_STEP
     f_ms, f_calls = phases["force"]
     peak, peak_src = measured_peak()
     force_avg_ms = f_ms / max(f_calls, 1)
     achieved = force_bytes / (force_avg_ms * 1e-3) / 1e9 if force_avg_ms > 0 else 0.0
-    tiled = bool(ctx.query("list_tile"))
     kern = (f"force_{a.force}_{'tile_' if tiled else ''}kernel<{'double' if s == 8 else 'float'},half={a.half_neigh},"
             f"gn={a.ghost_newton if a.half_neigh else 0}>")
     if a.force == "eam":                                          # two passes over the rows + fp traffic
@@ -316,6 +321,7 @@ def own_arm(a, n_gpus, rank, local_rank):
                 "frac": achieved / peak,
                 "traffic": profiled_traffic("force_lj_tile_f64" if tiled else ("force_lj_half_f64" if a.half_neigh else "force_lj_full_f64")),
                 "list_format": "tile-resident 16-bit rows, owner-computes" if tiled else "classic rows of global ids",
+                "fused_verlet": fused_verlet,
                 "algorithmic_bytes_per_launch": force_bytes, "avg_launch_ms": force_avg_ms, "launches_timed": f_calls,
                 "neighbors_per_atom": n_per_atom, "peak_source": peak_src,
                 "share_of_step": f_ms / max(sum(v[0] for v in phases.values()), 1e-12)}

@@ -204,6 +204,7 @@ struct mmd_ctx {
   // per-phase device timing of mmd_run (option "phase_timing"): marks[k] closes an interval of phase
   // mark_phase[k]; intervals are summed after the loop's final synchronisation.
   bool fuse_integrate = true;  // mmd_run: finalIntegrate(n) + initialIntegrate(n+1) in one kernel
+  bool fuse_force = true;      // mmd_run, tile-resident lists: ... and both inside the force kernel's epilogue
   bool phase_timing = false;
   std::vector<cudaEvent_t> marks;
   std::vector<int> mark_phase;
@@ -679,7 +680,7 @@ template <class T> struct Impl {
     return ev ? lj_launch<TPA, 0, 0, 1>(c) : lj_launch<TPA, 0, 0, 0>(c);
   }
   // tile-resident list: owner-computes shared-memory kernel (tile_kernels.cuh)
-  template <int EV, int UNI> static int lj_tile_launch(mmd_ctx* c, int half) {
+  template <int EV, int UNI, int INTEG> static int lj_tile_launch(mmd_ctx* c, int half, const VerletParams<T>& VP) {
     LJTileParams<T> P;
     P.cutforcesq = (T)c->lj_cut0; P.sigma6 = (T)c->lj_s60; P.epsilon = (T)c->lj_eps0;
     P.cutforcesq_tab = c->lj_cut.as<T>(); P.sigma6_tab = c->lj_s6.as<T>(); P.epsilon_tab = c->lj_eps.as<T>();
@@ -692,12 +693,24 @@ template <class T> struct Impl {
     const size_t smem = tile_smem_bytes<T>(g.hcap, !UNI);
     static bool attr_done = false;
     if (!attr_done) {
-      CU(cudaFuncSetAttribute(force_lj_tile_kernel<T, EV, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+      CU(cudaFuncSetAttribute(force_lj_tile_kernel<T, EV, UNI, INTEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
       attr_done = true;
     }
-    LAUNCH_SMEM(c, (force_lj_tile_kernel<T, EV, UNI>), g.ntiles, TILE_THREADS, smem, c->x.as<V>(), c->f.as<V>(), g,
+    LAUNCH_SMEM(c, (force_lj_tile_kernel<T, EV, UNI, INTEG>), g.ntiles, TILE_THREADS, smem, c->x.as<V>(), c->f.as<V>(), g,
                 c->tile_runs.as<int2>(), c->tile_center.as<int4>(), c->tile_info.as<int2>(), c->tile_slots.as<int>(),
-                c->trows.as<unsigned short>(), c->tnum.as<int2>(), c->tcap, c->nlocal, P, c->d_ev);
+                c->trows.as<unsigned short>(), c->tnum.as<int2>(), c->tcap, c->nlocal, P, VP, c->d_ev);
+    return MMD_OK;
+  }
+  // force of step n + finalIntegrate(n) + initialIntegrate(n+1) in one launch (tile-resident lists only); the new
+  // positions land in x_alt, which then becomes x
+  static int lj_tile_verlet(mmd_ctx* c, int half, int ev, double dt, double dtforce, double mass) {
+    VerletParams<T> VP;
+    VP.v = c->v.as<V>(); VP.x_out = c->x_alt.as<V>();
+    VP.dt = (T)dt; VP.dtforce = (T)dtforce; VP.mass = (T)mass;
+    if (ev) CU(cudaMemsetAsync(c->d_ev, 0, 3 * sizeof(double), c->stream));
+    if (c->lj_uniform) MM(ev ? (lj_tile_launch<1, 1, 1>(c, half, VP)) : (lj_tile_launch<0, 1, 1>(c, half, VP)));
+    else MM(ev ? (lj_tile_launch<1, 0, 1>(c, half, VP)) : (lj_tile_launch<0, 0, 1>(c, half, VP)));
+    std::swap(c->x, c->x_alt);
     return MMD_OK;
   }
 
@@ -711,8 +724,10 @@ template <class T> struct Impl {
       if (half && clear_f && c->nghost > 0)
         CU(cudaMemsetAsync(c->f.as<V>() + c->nlocal, 0, (size_t)c->nghost * sizeof(V), c->stream));
       if (ev) CU(cudaMemsetAsync(c->d_ev, 0, 2 * sizeof(double), c->stream));
-      if (c->lj_uniform) return ev ? lj_tile_launch<1, 1>(c, half) : lj_tile_launch<0, 1>(c, half);
-      return ev ? lj_tile_launch<1, 0>(c, half) : lj_tile_launch<0, 0>(c, half);
+      VerletParams<T> none;
+      memset(&none, 0, sizeof none);
+      if (c->lj_uniform) return ev ? lj_tile_launch<1, 1, 0>(c, half, none) : lj_tile_launch<0, 1, 0>(c, half, none);
+      return ev ? lj_tile_launch<1, 0, 0>(c, half, none) : lj_tile_launch<0, 0, 0>(c, half, none);
     }
     if (half && clear_f) CU(cudaMemsetAsync(c->f.p, 0, (size_t)(c->nlocal + c->nghost) * sizeof(V), c->stream));
     if (ev) CU(cudaMemsetAsync(c->d_ev, 0, 2 * sizeof(double), c->stream));
@@ -1086,6 +1101,11 @@ template <class T> struct Impl {
       }
     }
     c->neigh_rows = -1;  // lists are stale until the next build
+    // the second position buffer (Atom::sort scratch, target of the fused force+Verlet kernel) gets the ghost records
+    // too: remote halo unpacks only refresh x,y,z and rely on the type lane being in place
+    if (c->nghost > 0)
+      CU(cudaMemcpyAsync(c->x_alt.as<V>() + c->nlocal, c->x.as<V>() + c->nlocal, (size_t)c->nghost * sizeof(V),
+                         cudaMemcpyDeviceToDevice, c->stream));
     return MMD_OK;
   }
 
@@ -1121,15 +1141,21 @@ template <class T> struct Impl {
         MM(phase_mark(c, MMD_PHASE_NEIGH));
       }
       const int ev = p->thermo_nstat > 0 ? ((n + 1) % p->thermo_nstat == 0) : 0;
-      // tile-resident lists: every atom's force is complete after the kernel -- nothing to clear, nothing to send back
-      if (p->force_style == 0) MM(lj_async(c, p->halfneigh, p->ghost_newton, ev, !c->list_tile));
+      // tile-resident lists: every atom's force is complete after the kernel -- nothing to clear, nothing to send back,
+      // and the two velocity-Verlet halves that follow ride in the kernel's epilogue
+      const bool verlet_fused = c->fuse_force && c->fuse_integrate && c->list_tile && p->force_style == 0 && n < last;
+      if (verlet_fused) {
+        if (c->neigh_rows != c->nlocal) return set_err(MMD_ERR_STATE, "run: neighbor list is stale (build first)");
+        MM(lj_tile_verlet(c, p->halfneigh, ev, p->dt, p->dtforce, p->mass));
+      } else if (p->force_style == 0) MM(lj_async(c, p->halfneigh, p->ghost_newton, ev, !c->list_tile));
       else MM(eam_async(c, p->halfneigh, ev));
       MM(phase_mark(c, MMD_PHASE_FORCE));
       if (reverse_needed && !c->list_tile) {
         MM(reverse(c));
         MM(phase_mark(c, MMD_PHASE_COMM));
       }
-      if (n < last && c->fuse_integrate) MM(final_initial(c, p->dt, p->dtforce, ev != 0, p->mass));
+      if (verlet_fused) { /* done inside the force kernel */ }
+      else if (n < last && c->fuse_integrate) MM(final_initial(c, p->dt, p->dtforce, ev != 0, p->mass));
       else MM(final_(c, p->dtforce, ev != 0, p->mass));
       MM(phase_mark(c, MMD_PHASE_INTEGRATE));
       if (ev) {
@@ -1775,6 +1801,7 @@ int mmd_query_int(mmd_ctx* c, const char* key, long long* value) {
   else if (k == "exchange_received") *value = c->exch_received;
   else if (k == "nranks") *value = c->nranks;
   else if (k == "tile_lists") *value = c->tile_enable;
+  else if (k == "fuse_force") *value = c->fuse_force && c->fuse_integrate;
   else if (k == "list_tile") *value = c->list_tile;
   else if (k == "tile_ok") *value = c->tile_ok;
   else if (k == "tile_builds") *value = c->tile_builds;
@@ -1803,6 +1830,8 @@ int mmd_set_option(mmd_ctx* c, const char* key, long long value) {
     c->tile_build2 = value != 0;
   } else if (k == "fuse_integrate") {
     c->fuse_integrate = value != 0;
+  } else if (k == "fuse_force") {
+    c->fuse_force = value != 0;
   } else if (k == "phase_timing") {
     c->phase_timing = value != 0;
   } else if (k == "force_nonuniform") {  // testing: exercise the per-type table path

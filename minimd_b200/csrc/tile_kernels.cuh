@@ -725,12 +725,23 @@ __device__ __forceinline__ uint4 ldg_row8(const unsigned short* p) {
   return v;
 }
 
-template <class T, int EV, int UNIFORM>
+// INTEG = 1 fuses the velocity-Verlet updates that follow the force into the kernel's epilogue (F_i is in registers):
+// finalIntegrate of this step (ref/integrate.cpp:59-68, with sum m v^2 on thermo steps, ref/thermo.cpp:149-157) and
+// initialIntegrate of the next (:46-57), same operation order as final_initial_integrate_kernel.  Other CTAs still
+// read the old positions of their halo atoms, so the new positions go to a second buffer (x_out) that becomes the
+// atom array after the launch; f is not written.
+template <class T> struct VerletParams {
+  Vec4<T>* v;
+  Vec4<T>* x_out;
+  T dt, dtforce, mass;
+};
+
+template <class T, int EV, int UNIFORM, int INTEG>
 __global__ void __launch_bounds__(TILE_THREADS, 2)
 force_lj_tile_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, TileGeo g, const int2* __restrict__ tile_runs,
                      const int4* __restrict__ tile_center, const int2* __restrict__ tile_info, const int* __restrict__ slots,
                      const unsigned short* __restrict__ rows, const int2* __restrict__ row_atom, int tcap, int nlocal,
-                     LJTileParams<T> P, double* __restrict__ ev_out) {
+                     LJTileParams<T> P, VerletParams<T> VP, double* __restrict__ ev_out) {
   extern __shared__ __align__(16) unsigned char tile_smem_raw[];
   const int t = blockIdx.x;
   const int2 inf = tile_info[t];
@@ -759,7 +770,7 @@ force_lj_tile_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Til
   S.carve(tile_smem_raw, g.hcap, !UNIFORM);
   tile_stage<T, !UNIFORM>(S, g, t, inf.x, tile_runs, slots, x);
 
-  double eng = 0.0, vir = 0.0;
+  double eng = 0.0, vir = 0.0, ke = 0.0;
   for (; cr < TILE_NCENTER; cr += nw) {
     if (cr != w) {  // only when the block has fewer warps than centre pencils
       ce = tile_center[(size_t)t * TILE_NCENTER + cr];
@@ -851,15 +862,38 @@ force_lj_tile_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Til
         fz = group_sum<LJT_TPA>(fz);
       }
       if (id >= 0 && sub == 0) {
-        Vec4<T> out;
-        out.x = fx; out.y = fy; out.z = fz; out.w = (T)0;
-        f[id] = out;
+        if (INTEG) {
+          Vec4<T> vi = VP.v[id];
+          vi.x += VP.dtforce * fx;
+          vi.y += VP.dtforce * fy;
+          vi.z += VP.dtforce * fz;
+          if (EV) ke += (double)((vi.x * vi.x + vi.y * vi.y + vi.z * vi.z) * VP.mass);
+          vi.x += VP.dtforce * fx;
+          vi.y += VP.dtforce * fy;
+          vi.z += VP.dtforce * fz;
+          Vec4<T> xo;
+          xo.x = xi + VP.dt * vi.x;
+          xo.y = yi + VP.dt * vi.y;
+          xo.z = zi + VP.dt * vi.z;
+          xo.w = x[id].w;  // the type lane travels with the atom
+          VP.v[id] = vi;
+          VP.x_out[id] = xo;
+        } else {
+          Vec4<T> out;
+          out.x = fx; out.y = fy; out.z = fz; out.w = (T)0;
+          f[id] = out;
+        }
       }
     }
   }
   if (EV) {
-    const double v2[2] = {eng * P.e_scale, vir * P.v_scale};
-    block_accumulate<2>(v2, ev_out);
+    if (INTEG) {
+      const double v3[3] = {eng * P.e_scale, vir * P.v_scale, ke};
+      block_accumulate<3>(v3, ev_out);
+    } else {
+      const double v2[2] = {eng * P.e_scale, vir * P.v_scale};
+      block_accumulate<2>(v2, ev_out);
+    }
   }
 }
 
