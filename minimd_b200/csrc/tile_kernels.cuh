@@ -496,68 +496,107 @@ neigh_build_tile2_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* _
           // ---- flatten this block of candidates: tile-local index | own-bin bit | upper-stencil bit ----
           bool slow_blk = (MODE == 2);
           __syncwarp();
-          for (int k = lane; k < nblk32; k += 32) {
-            unsigned short e = (unsigned short)H;  // padding: the sentinel
-            if (k < nblk) {
-              const int n = cb0 + k;
-              int lo = 0, hi = nsr - 1;
-              while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (rpref[mid] <= n) lo = mid; else hi = mid - 1;
+          // one stencil range after the other (warp-uniform loop), 32 entries per step
+          for (int r = 0; r < nsr; r++) {
+            const int pref = rpref[r];
+            const int len = (r + 1 < nsr ? rpref[r + 1] : ncand) - pref;
+            if (len == 0 || pref + len <= cb0 || pref >= cb0 + nblk) continue;
+            const int start = rstart[r], info = rinfo[r];
+            for (int j = lane; j < len; j += 32) {
+              const int k = pref + j - cb0;
+              if (k >= 0 && k < nblk) {
+                const int lc = start + j;
+                const bool own_bin = (info & 0x40000000) && lc >= own_lo && lc < own_hi;
+                const bool upper = (info & 0x80000000) != 0 || ((info & 0x40000000) && lc >= own_hi);
+                ctab[k] = (unsigned short)(lc | (own_bin ? TB2_OWN : 0) | (upper ? TB2_UP : 0));
+                if (MODE == 1 && own_bin && lc >= ghost_lo) slow_blk = true;
               }
-              const int info = rinfo[lo];
-              const int lc = rstart[lo] + (n - rpref[lo]);
-              const bool own_bin = (info & 0x40000000) && lc >= own_lo && lc < own_hi;
-              const bool upper = (info & 0x80000000) != 0 || ((info & 0x40000000) && lc >= own_hi);
-              e = (unsigned short)(lc | (own_bin ? TB2_OWN : 0) | (upper ? TB2_UP : 0));
-              if (MODE == 1 && own_bin && lc >= ghost_lo) slow_blk = true;
             }
-            ctab[k] = e;
           }
+          if (nblk + lane < nblk32) ctab[nblk + lane] = (unsigned short)H;  // padding: the sentinel
           slow_blk = __any_sync(0xffffffffu, slow_blk);
           __syncwarp();
 
-          for (int tt = 0; tt < nloc; tt++) {
-            const int li = i0 + tt;
-            const float xi = sx[li], yi = sy[li], zi = sz[li];
-            const int ti = UC ? 0 : (int)st[li];
-            unsigned short* rowp = rows + (size_t)(q_i0 + tt) * tcap;
-            const int n_s = __shfl_sync(0xffffffffu, my_n, tt), h_s = __shfl_sync(0xffffffffu, my_h, tt);
-            int n_t = n_s, h_t = h_s;
+          // atoms are swept in pairs: the 32 candidates of a sweep are fetched once and tested against both
+          for (int tt = 0; tt < nloc; tt += 2) {
+            const int na = min(2, nloc - tt);
+            const int liA = i0 + tt, liB = i0 + min(tt + 1, nloc - 1);
+            const float xA = sx[liA], yA = sy[liA], zA = sz[liA], xB = sx[liB], yB = sy[liB], zB = sz[liB];
+            const int tA = UC ? 0 : (int)st[liA], tB = UC ? 0 : (int)st[liB];
+            unsigned short* rowA = rows + (size_t)(q_i0 + tt) * tcap;
+            unsigned short* rowB = rowA + tcap;
+            const int nA_s = __shfl_sync(0xffffffffu, my_n, tt), hA_s = __shfl_sync(0xffffffffu, my_h, tt);
+            const int nB_s = __shfl_sync(0xffffffffu, my_n, (tt + 1) & 31), hB_s = __shfl_sync(0xffffffffu, my_h, (tt + 1) & 31);
+            int nA = nA_s, hA = hA_s, nB = nB_s, hB = hB_s;
             bool redo = slow_blk;
             if (!slow_blk) {
               // ---- lean loop: FP32 decision, no ids.  key = index | class bits; with thr = li | OWN:
               //      key == thr <=> the atom itself;  key > thr <=> upper stencil half, or own bin and j > i ----
               bool closeany = false;
-              const int thr = li | TB2_OWN;
+              const int thrA = liA | TB2_OWN, thrB = liB | TB2_OWN;
+              const bool two = na == 2;
               for (int k0 = 0; k0 < nblk32; k0 += 32) {
                 const int key = ctab[k0 + lane] & 0x7fff;
                 const int lc = key & 0x1fff;
-                const float dx = xi - sx[lc], dy = yi - sy[lc], dz = zi - sz[lc];
-                float fc = fcut0;
-                if (!UC) fc = (float)__ldg(&cutneighsq[ti * ntypes + (int)st[lc]]);
-                bool ok;
-                if (sizeof(T) == 4) {
-                  ok = rsq_unfused(dx, dy, dz) <= fc;
-                } else {
-                  const float d = (dx * dx + dy * dy + dz * dz) - fc;
-                  ok = d < -band;
-                  closeany = closeany || (fabsf(d) <= band);
+                const float cxj = sx[lc], cyj = sy[lc], czj = sz[lc];
+                float fcA = fcut0, fcB = fcut0;
+                if (!UC) {
+                  const int tj = (int)st[lc];
+                  fcA = (float)__ldg(&cutneighsq[tA * ntypes + tj]);
+                  fcB = (float)__ldg(&cutneighsq[tB * ntypes + tj]);
                 }
-                ok = ok && key != thr;
-                const unsigned m = __ballot_sync(0xffffffffu, ok);
-                const bool half = MODE == 1 ? key > thr : true;
-                const unsigned mh = MODE == 0 ? m : __ballot_sync(0xffffffffu, ok && half);
-                if (ok) {
-                  const int pos = n_t + __popc(m & lt_mask);
-                  if (pos < tcap) rowp[pos] = (unsigned short)(lc | ((MODE != 0 && half) ? TILE_HALF_BIT : 0));
+                bool okA, okB;
+                {
+                  const float dx = xA - cxj, dy = yA - cyj, dz = zA - czj;
+                  if (sizeof(T) == 4) {
+                    okA = rsq_unfused(dx, dy, dz) <= fcA;
+                  } else {
+                    const float d = (dx * dx + dy * dy + dz * dz) - fcA;
+                    okA = d < -band;
+                    closeany = closeany || (fabsf(d) <= band);
+                  }
                 }
-                n_t += __popc(m);
-                h_t += __popc(mh);
+                {
+                  const float dx = xB - cxj, dy = yB - cyj, dz = zB - czj;
+                  if (sizeof(T) == 4) {
+                    okB = rsq_unfused(dx, dy, dz) <= fcB;
+                  } else {
+                    const float d = (dx * dx + dy * dy + dz * dz) - fcB;
+                    okB = d < -band;
+                    closeany = closeany || (two && fabsf(d) <= band);
+                  }
+                }
+                okA = okA && key != thrA;
+                okB = okB && key != thrB && two;
+                const unsigned mA = __ballot_sync(0xffffffffu, okA);
+                const unsigned mB = __ballot_sync(0xffffffffu, okB);
+                const bool halfA = MODE == 1 ? key > thrA : true, halfB = MODE == 1 ? key > thrB : true;
+                const unsigned mhA = MODE == 0 ? mA : __ballot_sync(0xffffffffu, okA && halfA);
+                const unsigned mhB = MODE == 0 ? mB : __ballot_sync(0xffffffffu, okB && halfB);
+                if (okA) {
+                  const int pos = nA + __popc(mA & lt_mask);
+                  if (pos < tcap) rowA[pos] = (unsigned short)(lc | ((MODE != 0 && halfA) ? TILE_HALF_BIT : 0));
+                }
+                if (okB) {
+                  const int pos = nB + __popc(mB & lt_mask);
+                  if (pos < tcap) rowB[pos] = (unsigned short)(lc | ((MODE != 0 && halfB) ? TILE_HALF_BIT : 0));
+                }
+                nA += __popc(mA); hA += __popc(mhA);
+                nB += __popc(mB); hB += __popc(mhB);
               }
               redo = sizeof(T) == 8 && __any_sync(0xffffffffu, closeany);
             }
             if (redo) {
+              nA = nA_s; hA = hA_s; nB = nB_s; hB = hB_s;
+            }
+            for (int a = 0; redo && a < na; a++) {
+              const int li = a ? liB : liA;
+              const float xi = a ? xB : xA, yi = a ? yB : yA, zi = a ? zB : zA;
+              const int ti = a ? tB : tA;
+              unsigned short* rowp = a ? rowB : rowA;
+              const int n_s = a ? nB_s : nA_s, h_s = a ? hB_s : hA_s;
+              int n_t = n_s, h_t = h_s;
+              {
               // ---- general loop: same sweep with ids at hand (exact FP64 test inside the band, ghost and j>i filters) ----
               n_t = n_s;
               h_t = h_s;
@@ -608,8 +647,11 @@ neigh_build_tile2_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* _
                 n_t += __popc(m);
                 h_t += __popc(mh);
               }
+                          }
+              if (a) { nB = n_t; hB = h_t; } else { nA = n_t; hA = h_t; }
             }
-            if (lane == tt) { my_n = n_t; my_h = h_t; }
+            if (lane == tt) { my_n = nA; my_h = hA; }
+            if (na == 2 && lane == tt + 1) { my_n = nB; my_h = hB; }
           }
         }
         if (lane < nloc) {
