@@ -269,6 +269,8 @@ def own_arm(a, n_gpus, rank, local_rank):
     if a.tpa:
         ctx.set_option("lj_threads_per_atom", a.tpa)
     ctx.set_option("tile_lists", a.tile)      # effective from the next neighbor build (inside the warm-up)
+    if not a.p2p:
+        ctx.set_option("p2p_halo", 0)
     natoms = sim.geti("natoms")
     stream = torch.cuda.ExternalStream(ctx.stream)
 
@@ -398,6 +400,9 @@ def own_arm(a, n_gpus, rank, local_rank):
         "roofline": roofline, "step_roofline": step_roofline, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clk, "thermo_last": {"step": st[-1], "T": T[-1], "U": U[-1], "P": P[-1]} if st else None,
         "counts": {"nlocal_rank0": nlocal, "nghost_rank0": sim.geti("nghost"), "maxneighs": sim.geti("maxneighs")},
+        "halo_transport": ("none (single rank: device-local self swaps)" if n_gpus == 1 else
+                           ("peer-memory windows over NVLink (CUDA IPC), fused pack+remote store / wait+unpack kernels"
+                            if ctx.query("p2p_active") else "NCCL send/recv + pack/unpack kernels")),
     }
     if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline:
         result["cpu_baseline"] = cpu_baseline(a, 1, MD_STEPS_PER_STEP)
@@ -425,6 +430,7 @@ def main():
     ap.add_argument("--tpa", type=int, default=0, help="lanes per atom in the force kernel (0 = library default)")
     ap.add_argument("--tile", type=int, default=1, help="1: tile-resident neighbor lists + shared-memory force kernel (default); "
                                                         "0: classic rows of global ids (gather / scatter kernels)")
+    ap.add_argument("--p2p", type=int, default=1, help="N>1: 1 = forward halo over peer-memory windows (default), 0 = NCCL send/recv")
     ap.add_argument("--no-e2e", dest="no_e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     a = ap.parse_args()

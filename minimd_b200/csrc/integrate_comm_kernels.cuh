@@ -227,6 +227,90 @@ __global__ void halo_pack_x_pair_kernel(const Vec4<T>* __restrict__ x, SwapPairD
   buf[(size_t)3 * g + 1] = p.y;
   buf[(size_t)3 * g + 2] = p.z;
 }
+// ---------------------------------------------------------------------------------------
+// Forward halo over peer memory (NVLink / NVSwitch), one rank per GPU.
+// Every rank owns a receive window that its neighbors map through CUDA IPC.  The sender's kernel packs the
+// positions of both swaps of a dimension (Atom::pack_comm, ref/atom.cpp:135-151) and stores them straight into the
+// two neighbors' windows; the last block to finish publishes the call's epoch in the neighbors' flag words
+// (system-scope release).  The receiver's unpack kernel spins on its own flag words (system-scope acquire) and
+// then scatters the window into the ghost slots (Atom::unpack_comm, :153-170).  No host round trip, no staging
+// copy, no NCCL launch: two short kernels per dimension.  Windows are double-buffered by epoch parity; a sender
+// can reuse a buffer only two calls later, after it has itself consumed the receiver's next message, which the
+// receiver sent after finishing the unpack of the buffer in question (stream order on both sides).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <class T>
+__global__ void halo_p2p_send_kernel(const Vec4<T>* __restrict__ x, SwapPairDev sp, T xprd, T yprd, T zprd,
+                                     T* __restrict__ dst0, T* __restrict__ dst1, unsigned long long* flag0,
+                                     unsigned long long* flag1, unsigned long long epoch, unsigned* __restrict__ done) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  int k = g, s = 0;
+  if (k >= sp.count[0]) { k -= sp.count[0]; s = 1; }
+  if (k < sp.count[s]) {
+    Vec4<T> p = x[sp.list[s][k]];
+    if (sp.any[s]) {
+      p.x = p.x + sp.flag[s][0] * xprd;
+      p.y = p.y + sp.flag[s][1] * yprd;
+      p.z = p.z + sp.flag[s][2] * zprd;
+    }
+    T* d = (s ? dst1 : dst0) + (size_t)3 * k;
+    d[0] = p.x;
+    d[1] = p.y;
+    d[2] = p.z;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(done, 1u);
+    if (t == gridDim.x - 1) {
+      *done = 0u;
+      __threadfence_system();
+      st_release_sys(flag0, epoch);
+      st_release_sys(flag1, epoch);
+    }
+  }
+}
+
+// status |= 4 when a neighbor's message did not arrive within ~2 s (a rank died or the ranks diverged)
+template <class T, int ZERO_F>
+__global__ void halo_p2p_unpack_kernel(Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, int first0, int n0, int first1,
+                                       int n1, const T* __restrict__ src0, const T* __restrict__ src1,
+                                       const unsigned long long* flag0, const unsigned long long* flag1,
+                                       unsigned long long epoch, int* __restrict__ status) {
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag0) < epoch || ld_acquire_sys(flag1) < epoch) {
+      if (clock64() - t0 > 4000000000ll) {
+        atomicOr(status, 4);
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n0 + n1) return;
+  const int dst = g < n0 ? first0 + g : first1 + (g - n0);
+  const T* b = g < n0 ? src0 + (size_t)3 * g : src1 + (size_t)3 * (g - n0);
+  Vec4<T> p = x[dst];  // keeps the type lane set by borders
+  p.x = __ldcg(b + 0);  // the window is written by another GPU: read it from L2, never from a stale L1 line
+  p.y = __ldcg(b + 1);
+  p.z = __ldcg(b + 2);
+  x[dst] = p;
+  if (ZERO_F) {
+    Vec4<T> z; z.x = z.y = z.z = z.w = (T)0;
+    f[dst] = z;
+  }
+}
+
 template <class T, int ZERO_F>
 __global__ void halo_unpack_x_pair_kernel(Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, int first0, int n0, int first1,
                                           int n1, const T* __restrict__ buf) {

@@ -187,6 +187,14 @@ struct mmd_ctx {
   ncclComm_t nccl = nullptr;
 #endif
   int nranks = 1, rank = 0;
+  // forward halo over peer memory (integrate_comm_kernels.cuh): own receive window + the neighbors' mapped windows
+  bool p2p_enable = true;   // option "p2p_halo"
+  bool p2p_on = false;
+  unsigned char* win = nullptr;
+  std::vector<unsigned char*> peer_win;
+  unsigned* d_done = nullptr;
+  unsigned long long p2p_epoch[MMD_MAX_SWAPS] = {0};
+  long long p2p_calls = 0;
 
   // device scalars + pinned mirror
   // d_scal ints : [0] status, [1] max_n, [2] max_bin, [3] border total 0, [4] border total 1, [5] scan total,
@@ -280,6 +288,19 @@ __global__ void rows_restride_kernel(const int* __restrict__ src, int rows, int 
   if (idx >= (long long)rows * ncopy) return;
   const int r = (int)(idx / ncopy), k = (int)(idx % ncopy);
   dst[(size_t)r * dst_stride + k] = src[(size_t)r * src_stride + k];
+}
+
+// ---------------------------------------------------------------------------------------
+// receive window of the peer-memory forward halo: 6 flag words (256 B apart), then [parity][swap] regions
+// ---------------------------------------------------------------------------------------
+static const int P2P_SWAPS = 6;
+static const size_t P2P_REGION_ATOMS = 262144;
+static const size_t P2P_FLAG_BYTES = 4096;
+static const size_t P2P_REGION_BYTES = P2P_REGION_ATOMS * 3 * sizeof(double);
+static const size_t P2P_WIN_BYTES = P2P_FLAG_BYTES + 2 * P2P_SWAPS * P2P_REGION_BYTES;
+static inline unsigned long long* p2p_flag(unsigned char* win, int w) { return reinterpret_cast<unsigned long long*>(win + (size_t)w * 256); }
+static inline unsigned char* p2p_region(unsigned char* win, int parity, int w) {
+  return win + P2P_FLAG_BYTES + ((size_t)parity * P2P_SWAPS + w) * P2P_REGION_BYTES;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -438,6 +459,7 @@ template <class T> struct Impl {
     CU(cudaStreamSynchronize(c->stream));
     c->max_bin_seen = std::max(c->max_bin_seen, c->h_scal[2]);
     if (c->h_scal[0] & 1) return set_err(MMD_ERR_STATE, "atom outside the bin grid (lost atom / bad coordinates)");
+    if (c->h_scal[0] & 4) return set_err(MMD_ERR_STATE, "forward halo: a neighbor rank's message did not arrive (peer-memory path timed out)");
     return MMD_OK;
   }
 
@@ -949,6 +971,25 @@ template <class T> struct Impl {
         if (nsw != 2) return set_err(MMD_ERR_STATE, "communicate: odd swap count");
         const SwapPairDev sp = pair_desc(c, w, 2);
         const int ns0 = c->sw[w].sendnum, ns1 = c->sw[w + 1].sendnum, nr0 = c->sw[w].recvnum, nr1 = c->sw[w + 1].recvnum;
+        if (c->p2p_on && c->swaps.nswap <= P2P_SWAPS) {
+          // peer-memory path: pack straight into the neighbors' windows, then wait for theirs and unpack
+          if ((size_t)std::max(std::max(ns0, ns1), std::max(nr0, nr1)) > P2P_REGION_ATOMS)
+            return set_err(MMD_ERR_STATE, "communicate: halo message exceeds the peer window (set option p2p_halo to 0)");
+          const unsigned long long epoch = ++c->p2p_epoch[w];
+          const int par = (int)(epoch & 1ull);
+          unsigned char* pw0 = c->peer_win[c->swaps.sendproc[w]];
+          unsigned char* pw1 = c->peer_win[c->swaps.sendproc[w + 1]];
+          LAUNCH(c, halo_p2p_send_kernel<T>, std::max(1, div_up(ns0 + ns1, TPB)), TPB, c->x.as<V>(), sp, px, py, pz,
+                 reinterpret_cast<T*>(p2p_region(pw0, par, w)), reinterpret_cast<T*>(p2p_region(pw1, par, w + 1)),
+                 p2p_flag(pw0, w), p2p_flag(pw1, w + 1), epoch, c->d_done + w / 2);
+          const T* s0 = reinterpret_cast<const T*>(p2p_region(c->win, par, w));
+          const T* s1 = reinterpret_cast<const T*>(p2p_region(c->win, par, w + 1));
+          const int ug = std::max(1, div_up(nr0 + nr1, TPB));
+          if (zero_ghost_f) LAUNCH(c, (halo_p2p_unpack_kernel<T, 1>), ug, TPB, c->x.as<V>(), c->f.as<V>(), c->sw[w].firstrecv, nr0, c->sw[w + 1].firstrecv, nr1, s0, s1, p2p_flag(c->win, w), p2p_flag(c->win, w + 1), epoch, c->d_scal + 0);
+          else LAUNCH(c, (halo_p2p_unpack_kernel<T, 0>), ug, TPB, c->x.as<V>(), c->f.as<V>(), c->sw[w].firstrecv, nr0, c->sw[w + 1].firstrecv, nr1, s0, s1, p2p_flag(c->win, w), p2p_flag(c->win, w + 1), epoch, c->d_scal + 0);
+          c->p2p_calls++;
+          continue;
+        }
         MM(c->sendbuf.reserve((size_t)3 * (ns0 + ns1) * sizeof(T), c->stream, 0, 1.5));
         MM(c->recvbuf.reserve((size_t)3 * (nr0 + nr1) * sizeof(T), c->stream, 0, 1.5));
         LAUNCH(c, halo_pack_x_pair_kernel<T>, div_up(ns0 + ns1, TPB), TPB, c->x.as<V>(), sp, px, py, pz, c->sendbuf.as<T>());
@@ -1294,6 +1335,52 @@ template <class T> static bool all_equal(const T* a, int n) {
   return true;
 }
 
+#ifdef MMD_WITH_NCCL
+// Map every rank's receive window into every other rank (CUDA IPC, one node).  All-or-nothing: if any rank cannot
+// export or import a window, all ranks keep the NCCL path (p2p_on stays false, query "p2p_active").
+static int p2p_setup(mmd_ctx* c) {
+  const int n = c->nranks;
+  struct Slot { cudaIpcMemHandle_t h; int ok; int pad[15]; };  // 128 bytes
+  static_assert(sizeof(Slot) == 128, "slot size");
+  Slot mine;
+  memset(&mine, 0, sizeof mine);
+  bool ok = cudaMalloc(&c->win, P2P_WIN_BYTES) == cudaSuccess;
+  if (ok) ok = cudaMemset(c->win, 0, P2P_WIN_BYTES) == cudaSuccess;
+  if (ok) ok = cudaMalloc(&c->d_done, 16 * sizeof(unsigned)) == cudaSuccess && cudaMemset(c->d_done, 0, 16 * sizeof(unsigned)) == cudaSuccess;
+  if (ok) ok = cudaIpcGetMemHandle(&mine.h, c->win) == cudaSuccess;
+  cudaGetLastError();
+  mine.ok = ok ? 1 : 0;
+  Slot* d_slots = nullptr;
+  CU(cudaMalloc(&d_slots, (size_t)n * sizeof(Slot)));
+  CU(cudaMemcpy(d_slots + c->rank, &mine, sizeof(Slot), cudaMemcpyHostToDevice));
+  NC(ncclAllGather(d_slots + c->rank, d_slots, sizeof(Slot), ncclChar, c->nccl, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  std::vector<Slot> all(n);
+  CU(cudaMemcpy(all.data(), d_slots, (size_t)n * sizeof(Slot), cudaMemcpyDeviceToHost));
+  for (int r = 0; r < n; r++) ok = ok && all[r].ok == 1;
+  c->peer_win.assign(n, nullptr);
+  if (ok) {
+    for (int r = 0; r < n && ok; r++) {
+      if (r == c->rank) { c->peer_win[r] = c->win; continue; }
+      void* q = nullptr;
+      if (cudaIpcOpenMemHandle(&q, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); }
+      c->peer_win[r] = (unsigned char*)q;
+    }
+  }
+  // second round: did everybody import everything?
+  int* d_flag = reinterpret_cast<int*>(d_slots);
+  const int v = ok ? 1 : 0;
+  CU(cudaMemcpy(d_flag, &v, sizeof(int), cudaMemcpyHostToDevice));
+  NC(ncclAllReduce(d_flag, d_flag, 1, ncclInt, ncclMin, c->nccl, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  int all_ok = 0;
+  CU(cudaMemcpy(&all_ok, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  CU(cudaFree(d_slots));
+  c->p2p_on = all_ok == 1;
+  return MMD_OK;
+}
+#endif
+
 extern "C" {
 
 const char* mmd_last_error(void) { return g_err; }
@@ -1356,6 +1443,10 @@ int mmd_ctx_destroy(mmd_ctx* c) {
                     &c->tnum};
   for (DevBuf* b : bufs) b->release();
   for (int w = 0; w < MMD_MAX_SWAPS; w++) c->sw[w].list.release();
+  for (int r = 0; r < (int)c->peer_win.size(); r++)
+    if (c->peer_win[r] && c->peer_win[r] != c->win) cudaIpcCloseMemHandle(c->peer_win[r]);
+  if (c->win) cudaFree(c->win);
+  if (c->d_done) cudaFree(c->d_done);
 #ifdef MMD_WITH_NCCL
   if (c->nccl) ncclCommDestroy(c->nccl);
 #endif
@@ -1696,6 +1787,7 @@ int mmd_comm_nccl_init(mmd_ctx* c, const void* id128, int rank, int nranks) {
   NC(ncclCommInitRank(&c->nccl, nranks, id, rank));
   c->rank = rank;
   c->nranks = nranks;
+  if (nranks > 1 && c->p2p_enable) MM(p2p_setup(c));
   return MMD_OK;
 #else
   (void)id128; (void)rank; (void)nranks;
@@ -1800,6 +1892,8 @@ int mmd_query_int(mmd_ctx* c, const char* key, long long* value) {
   else if (k == "exchange_sent") *value = c->exch_sent;
   else if (k == "exchange_received") *value = c->exch_received;
   else if (k == "nranks") *value = c->nranks;
+  else if (k == "p2p_active") *value = c->p2p_on;
+  else if (k == "p2p_calls") *value = c->p2p_calls;
   else if (k == "tile_lists") *value = c->tile_enable;
   else if (k == "fuse_force") *value = c->fuse_force && c->fuse_integrate;
   else if (k == "list_tile") *value = c->list_tile;
@@ -1826,6 +1920,9 @@ int mmd_set_option(mmd_ctx* c, const char* key, long long value) {
     c->eam_tpa = (int)value;
   } else if (k == "tile_lists") {  // 1: tile-resident lists + shared-memory force kernels where they apply; 0: classic rows
     c->tile_enable = value != 0;  // takes effect at the next neighbor build
+  } else if (k == "p2p_halo") {  // 0: forward halo through NCCL send/recv even when peer windows are mapped
+    c->p2p_enable = value != 0;
+    if (!c->p2p_enable) c->p2p_on = false;
   } else if (k == "tile_build2") {
     c->tile_build2 = value != 0;
   } else if (k == "fuse_integrate") {

@@ -31,6 +31,7 @@ CASES = [
     (2, ["--cells", 12, 12, 24, "--half_neigh", 1, "--ghost_newton", 0]),
     (2, ["--cells", 10, 10, 20, "--force", "eam", "--half_neigh", 0]),
     (2, ["--cells", 10, 10, 20, "--force", "eam", "--half_neigh", 1]),
+    (2, ["--cells", 12, 12, 24, "--p2p", 0]),
     (4, ["--cells", 12, 24, 24]),
     (8, ["--cells", 24, 24, 24]),
     (8, ["--cells", 20, 20, 20, "--force", "eam", "--half_neigh", 0]),
@@ -44,3 +45,5 @@ def test_multi_gpu_matches_single_rank_oracle(n, extra):
     res = launch(n, extra, 29600 + n)
     assert res["ok"], res
     assert res["ranks"] == n and res["migrated_atoms"] > 0
+    if "--p2p" in extra:
+        assert res["p2p_active"] == 0 and res["p2p_calls"] == 0

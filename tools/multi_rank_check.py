@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--ghost_newton", type=int, default=1)
     ap.add_argument("--precision", default="f64")
     ap.add_argument("--tol", type=float, default=1e-9)
+    ap.add_argument("--p2p", type=int, default=1, help="1: forward halo over peer-memory windows; 0: NCCL send/recv")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -49,6 +50,8 @@ def main():
         if a.force == "eam":
             args += ["--eam_file", eam_file(td)]
         sim = Simulation(args, a.precision, rank=rank, nranks=world, device=local, nccl_id=idt.cpu().numpy().tobytes())
+        if not a.p2p:
+            sim.context().set_option("p2p_halo", 0)
         neigh0 = torch.tensor([sim.geti("total_neigh")], dtype=torch.float64, device="cuda")
         dist.all_reduce(neigh0)
         ms = sim.run()
@@ -57,6 +60,7 @@ def main():
                             sim.context().query("exchange_sent")], dtype=torch.float64, device="cuda")
         dist.all_reduce(cnt)
         grid = [sim.geti(f"procgrid{d}") for d in range(3)]
+        p2p = [sim.context().query("p2p_active"), sim.context().query("p2p_calls")]
         sim.close()
     ok, res = True, None
     if rank == 0:
@@ -78,7 +82,7 @@ def main():
               and int(cnt[0].item()) == o.geti("natoms") and counts_ok)
         res = {"ok": bool(ok), "ranks": world, "procgrid": grid, "cells": a.cells, "force": a.force, "errs": errs,
                "natoms": int(cnt[0].item()), "neigh_step0": [int(neigh0.item()), n0], "neigh_end": [int(cnt[1].item()), n1],
-               "nghost_sum": int(cnt[2].item()), "migrated_atoms": int(cnt[3].item()), "device_ms": ms,
+               "nghost_sum": int(cnt[2].item()), "migrated_atoms": int(cnt[3].item()), "device_ms": ms, "p2p_active": p2p[0], "p2p_calls": p2p[1],
                "last": [st[-1], T[-1], U[-1], P[-1]]}
         print(json.dumps(res), flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
