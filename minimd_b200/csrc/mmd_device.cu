@@ -18,6 +18,7 @@
 #include "neighbor_kernels.cuh"
 #include "scan.cuh"
 #include "tile_kernels.cuh"
+#include "tile_eam_kernels.cuh"
 
 #ifdef MMD_WITH_NCCL
 #include <nccl.h>
@@ -152,6 +153,7 @@ struct mmd_ctx {
 
   // tile-resident lists (tile_kernels.cuh): 16-bit tile-local rows + shared-memory force kernels
   bool tile_enable = true;  // option "tile_lists"
+  bool tile_eam = false;    // option "tile_eam": tile-resident lists for the EAM force too
   bool tile_ok = false;     // bin grid / stencil admit the tiling (decided by mmd_neigh_setup)
   bool tile_build2 = true;  // option "tile_build2": CTA-per-tile build from shared memory (0: warp-per-bin build)
   bool list_tile = false;   // format of the current list
@@ -473,7 +475,9 @@ template <class T> struct Impl {
   }
 
   // ---- neighbor build ------------------------------------------------------------------
-  static bool want_tile(mmd_ctx* c) { return c->tile_enable && c->tile_ok && !c->have_eam; }
+  // EAM: the owner-computes passes (tile_eam_kernels.cuh) evaluate every pair twice and the pair math is table-bound --
+  // measured slower than the classic half-list path at -s 64 (1.38 vs 0.99 ms per step), so they are opt-in ("tile_eam")
+  static bool want_tile(mmd_ctx* c) { return c->tile_enable && c->tile_ok && (!c->have_eam || c->tile_eam); }
 
   // tile-resident build (tile_kernels.cuh).  *done = false when the tiling does not fit this state (halo window
   // larger than the shared-memory capacity, stencil leaving the grid): the caller builds classic rows instead.
@@ -852,13 +856,45 @@ template <class T> struct Impl {
     if (c->eam_uniform) return ev ? eam_launch<TPA, 1, 1>(c, half) : eam_launch<TPA, 0, 1>(c, half);
     return ev ? eam_launch<TPA, 1, 0>(c, half) : eam_launch<TPA, 0, 0>(c, half);
   }
+  // tile-resident list: owner-computes shared-memory passes (tile_eam_kernels.cuh)
+  template <int EV, int UNI> static int eam_tile_launch(mmd_ctx* c, int half) {
+    const EAMTables<T> E = eam_tables(c);
+    const TileGeo& g = c->tgeo;
+    const size_t sm1 = eam_tile_smem_bytes<T>(g.hcap, 1), sm2 = eam_tile_smem_bytes<T>(g.hcap, 2);
+    if (sm2 > (size_t)(227 * 1024 - 2048)) return set_err(MMD_ERR_STATE, "force_eam: halo window too large for the tile kernels");
+    static bool attr_done = false;
+    if (!attr_done) {
+      CU(cudaFuncSetAttribute(eam_tile_kernel<T, 1, EV, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+      CU(cudaFuncSetAttribute(eam_tile_kernel<T, 2, EV, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+      attr_done = true;
+    }
+    // ghosts receive no force in this scheme; keep their f at zero so that a following reverse halo is a no-op
+    if (half && c->nghost > 0) CU(cudaMemsetAsync(c->f.as<V>() + c->nlocal, 0, (size_t)c->nghost * sizeof(V), c->stream));
+#define EAMT_ARGS                                                                                                     \
+  c->x.as<V>(), c->f.as<V>(), g, c->tile_runs.as<int2>(), c->tile_center.as<int4>(), c->tile_info.as<int2>(),         \
+      c->tile_slots.as<int>(), c->trows.as<unsigned short>(), c->tnum.as<int2>(), c->tcap, c->nlocal, E, c->fp.as<T>(), \
+      c->d_ev
+    LAUNCH_SMEM(c, (eam_tile_kernel<T, 1, EV, UNI>), g.ntiles, TILE_THREADS, sm1, EAMT_ARGS);
+    MM(forward_scalar(c, c->fp.as<T>()));
+    LAUNCH_SMEM(c, (eam_tile_kernel<T, 2, EV, UNI>), g.ntiles, TILE_THREADS, sm2, EAMT_ARGS);
+#undef EAMT_ARGS
+    return MMD_OK;
+  }
+
   static int eam_async(mmd_ctx* c, int half, int ev) {
-    MM(ensure_classic(c));
     if (!c->have_eam) return set_err(MMD_ERR_STATE, "force_eam: mmd_force_eam_setup missing");
     if (c->neigh_rows != c->nlocal) return set_err(MMD_ERR_STATE, "force_eam: neighbor list is stale (build first)");
     MM(c->rho.reserve((size_t)c->cap * sizeof(T), c->stream));
     MM(c->fp.reserve((size_t)c->cap * sizeof(T), c->stream));
     if (ev) CU(cudaMemsetAsync(c->d_ev, 0, 4 * sizeof(double), c->stream));
+    if (c->list_tile) {
+      if ((half != 0) != (c->list_half != 0)) return set_err(MMD_ERR_STATE, "force_eam: list was built for the other neighbor style");
+      if (eam_tile_smem_bytes<T>(c->tgeo.hcap, 2) <= (size_t)(227 * 1024 - 2048)) {
+        if (c->eam_uniform) return ev ? eam_tile_launch<1, 1>(c, half) : eam_tile_launch<0, 1>(c, half);
+        return ev ? eam_tile_launch<1, 0>(c, half) : eam_tile_launch<0, 0>(c, half);
+      }
+      MM(ensure_classic(c));  // window too large for the pair pass: export once, continue on classic rows
+    }
     switch (c->eam_tpa) {
       case 1: return eam_dispatch<1>(c, half, ev);
       case 2: return eam_dispatch<2>(c, half, ev);
@@ -1920,6 +1956,8 @@ int mmd_set_option(mmd_ctx* c, const char* key, long long value) {
     c->eam_tpa = (int)value;
   } else if (k == "tile_lists") {  // 1: tile-resident lists + shared-memory force kernels where they apply; 0: classic rows
     c->tile_enable = value != 0;  // takes effect at the next neighbor build
+  } else if (k == "tile_eam") {
+    c->tile_eam = value != 0;
   } else if (k == "p2p_halo") {  // 0: forward halo through NCCL send/recv even when peer windows are mapped
     c->p2p_enable = value != 0;
     if (!c->p2p_enable) c->p2p_on = false;

@@ -154,6 +154,7 @@ def test_coord2bin_edge_cases_bit_exact():
 def setup_lists(o, tile=1):
     c = context_from_oracle(o)
     c.set_option("tile_lists", tile)
+    c.set_option("tile_eam", tile)      # EAM uses classic rows unless asked (measured faster); the tests cover both
     c.exchange()
     c.borders()
     c.build(o.geti("halfneigh"), o.geti("ghost_newton"), 100)
@@ -232,12 +233,15 @@ def test_lj_per_type_tables_path(tile):
     assert abs(vir - o.getr("virial")) <= 1e-10 * abs(o.getr("eng_vdwl"))
 
 
+@pytest.mark.parametrize("tile", [1, 0])
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 @pytest.mark.parametrize("half", [1, 0])
 @pytest.mark.parametrize("uniform", [1, 0])
-def test_eam_force_energy_virial(half, uniform, prec):
+def test_eam_force_energy_virial(half, uniform, prec, tile):
+    """tile=1: both EAM passes as owner-computes shared-memory kernels on tile-resident rows; tile=0: classic rows."""
     o = melted(dict(nx=6, ny=6, nz=6, force="eam", halfneigh=half, ghost_newton=0), 20, prec)
-    c = setup_lists(o)
+    c = setup_lists(o, tile)
+    assert c.query("list_tile") == tile
     if not uniform:
         c.set_option("force_nonuniform", 1)
     o.seti("evflag", 1)
@@ -321,19 +325,18 @@ RUN_CASES = [
 @pytest.mark.parametrize("tile", [1, 0])
 @pytest.mark.parametrize("force,half,gn,prec,tol", RUN_CASES)
 def test_time_loop_matches_oracle(force, half, gn, prec, tol, tile):
-    if tile and force == "eam":
-        pytest.skip("EAM runs on classic rows")
     cfg = Config(nx=8, ny=8, nz=8, ntimes=100, force=force, halfneigh=half, ghost_newton=gn, thermo_nstat=10)
     o64 = Oracle(cfg, "f64")          # FP32 runs are judged against the FP64 oracle
     o = Oracle(cfg, prec)
     c = context_from_oracle(o)
     c.set_option("tile_lists", tile)
+    c.set_option("tile_eam", tile)
     c.exchange()
     c.borders()
     c.build(o.geti("halfneigh"), o.geti("ghost_newton"), 100)
-    assert c.query("list_tile") == (tile if force == "lj" else 0)
+    assert c.query("list_tile") == tile
     samples, ms = c.run(run_params(o, 100))
-    assert c.query("list_tile") == (tile if force == "lj" else 0)
+    assert c.query("list_tile") == tile
     got = thermo_from_samples(o, samples)
     o64.run(100)
     st, T, U, P = o64.thermo_log()
