@@ -146,6 +146,42 @@ __global__ void halo_forward_self_kernel(Vec4<T>* __restrict__ x, Vec4<T>* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// One-launch forward halo when every swap is a self swap (single rank): each ghost is resolved, at ghost-rebuild
+// time, to the LOCAL atom it ultimately copies and to the accumulated periodic shift (a ghost of a ghost made in the
+// y swap from an x-swap ghost carries both shifts).  Every swap shifts one coordinate only, so the composed copy
+// x[src] + shift*prd is bit-identical to the reference's six ordered swaps (ref/comm.cpp:276-317).
+// shift is packed as three 2-bit fields holding flag+1.
+// ---------------------------------------------------------------------------------------
+__global__ void ghost_resolve_kernel(const int* __restrict__ list, int count, int first, int nlocal, int fx, int fy, int fz,
+                                     int* __restrict__ src, int* __restrict__ shift) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const int s = list[k];
+  const int g = first + k - nlocal;
+  int sx = fx, sy = fy, sz = fz, from = s;
+  if (s >= nlocal) {
+    const int pk = shift[s - nlocal];
+    sx += (pk & 3) - 1; sy += ((pk >> 2) & 3) - 1; sz += ((pk >> 4) & 3) - 1;
+    from = src[s - nlocal];
+  }
+  src[g] = from;
+  shift[g] = (sx + 1) | ((sy + 1) << 2) | ((sz + 1) << 4);
+}
+template <class T>
+__global__ void halo_forward_resolved_kernel(Vec4<T>* __restrict__ x, int nlocal, int nghost, const int* __restrict__ src,
+                                             const int* __restrict__ shift, T xprd, T yprd, T zprd) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nghost) return;
+  Vec4<T> p = x[src[g]];
+  const int pk = shift[g];
+  const int sx = (pk & 3) - 1, sy = ((pk >> 2) & 3) - 1, sz = ((pk >> 4) & 3) - 1;
+  if (sx) p.x = p.x + sx * xprd;
+  if (sy) p.y = p.y + sy * yprd;
+  if (sz) p.z = p.z + sz * zprd;
+  x[nlocal + g] = p;
+}
+
 // self-swap reverse: f[list[k]] += f[first+k]  (pack_reverse + unpack_reverse fused).
 // REDG because the two swaps of a pair (and, in tiny boxes, one list) may name an atom twice.
 template <class T>

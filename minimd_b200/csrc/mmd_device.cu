@@ -182,6 +182,9 @@ struct mmd_ctx {
   mmd_swap_table swaps;
   SwapState sw[MMD_MAX_SWAPS];
   DevBuf border_tiles;  // 2 arrays of tile counts
+  DevBuf ghost_src, ghost_shift;  // single rank: every ghost resolved to its local source + periodic shift
+  bool ghosts_resolved = false;
+  bool fuse_halo = true;          // option "fuse_halo"
   DevBuf sendbuf, recvbuf;
   DevBuf exch_flag, exch_pos, exch_holes;
   long long exch_sent = 0, exch_received = 0;  // atoms migrated so far (introspection)
@@ -361,6 +364,7 @@ template <class T> struct Impl {
     CU(cudaStreamSynchronize(c->stream));
     c->nlocal = nlocal;
     c->neigh_rows = -1;  // lists and ghost tables refer to the previous atoms
+    c->ghosts_resolved = false;
     for (int w = 0; w < MMD_MAX_SWAPS; w++) c->sw[w].sendnum = c->sw[w].recvnum = c->sw[w].firstrecv = 0;
     return MMD_OK;
   }
@@ -995,6 +999,11 @@ template <class T> struct Impl {
   static int communicate(mmd_ctx* c, bool zero_ghost_f) {
     if (!c->have_comm) return set_err(MMD_ERR_STATE, "communicate: mmd_comm_setup missing");
     const T px = (T)c->prd[0], py = (T)c->prd[1], pz = (T)c->prd[2];
+    if (c->ghosts_resolved && !zero_ghost_f) {
+      LAUNCH(c, halo_forward_resolved_kernel<T>, div_up(c->nghost, TPB), TPB, c->x.as<V>(), c->nlocal, c->nghost,
+             c->ghost_src.as<int>(), c->ghost_shift.as<int>(), px, py, pz);
+      return MMD_OK;
+    }
     for (int w = 0; w < c->swaps.nswap; w += 2) {
       const int nsw = std::min(2, c->swaps.nswap - w);
       if (is_self(c, w) && (nsw < 2 || is_self(c, w + 1))) {
@@ -1178,6 +1187,23 @@ template <class T> struct Impl {
       }
     }
     c->neigh_rows = -1;  // lists are stale until the next build
+    // single rank: resolve every ghost to its local source so that the per-step forward halo is one launch
+    c->ghosts_resolved = false;
+    {
+      bool all_self = c->fuse_halo && c->nghost > 0;
+      for (int ws = 0; ws < c->swaps.nswap; ws++) all_self = all_self && is_self(c, ws);
+      if (all_self) {
+        MM(c->ghost_src.reserve((size_t)c->nghost * sizeof(int), c->stream, 0, 1.3));
+        MM(c->ghost_shift.reserve((size_t)c->nghost * sizeof(int), c->stream, 0, 1.3));
+        for (int ws = 0; ws < c->swaps.nswap; ws++) {
+          const int any = c->swaps.pbc_any[ws];
+          LAUNCH(c, ghost_resolve_kernel, div_up(c->sw[ws].sendnum, TPB), TPB, c->sw[ws].list.as<int>(), c->sw[ws].sendnum,
+                 c->sw[ws].firstrecv, c->nlocal, any ? c->swaps.pbc_flagx[ws] : 0, any ? c->swaps.pbc_flagy[ws] : 0,
+                 any ? c->swaps.pbc_flagz[ws] : 0, c->ghost_src.as<int>(), c->ghost_shift.as<int>());
+        }
+        c->ghosts_resolved = true;
+      }
+    }
     // the second position buffer (Atom::sort scratch, target of the fused force+Verlet kernel) gets the ghost records
     // too: remote halo unpacks only refresh x,y,z and rely on the type lane being in place
     if (c->nghost > 0)
@@ -1274,6 +1300,7 @@ template <class T> struct Impl {
   static int exchange(mmd_ctx* c) {
     MM(pbc(c));
     c->nghost = 0;  // ghosts are rebuilt by borders(); nlocal may change below
+    c->ghosts_resolved = false;
     for (int d = 0; d < 3; d++) {
       if (c->swaps.procgrid[d] <= 1) continue;
 #ifdef MMD_WITH_NCCL
@@ -1475,7 +1502,7 @@ int mmd_ctx_destroy(mmd_ctx* c) {
                     &c->tile_sums, &c->numneigh, &c->neighbors, &c->lj_cut, &c->lj_s6, &c->lj_eps, &c->eam_rho_val,
                     &c->eam_rho_der, &c->eam_z2_val, &c->eam_z2_der, &c->eam_frho_val, &c->eam_frho_der, &c->eam_cut,
                     &c->rho, &c->fp, &c->border_tiles, &c->sendbuf, &c->recvbuf, &c->exch_flag, &c->exch_pos,
-                    &c->exch_holes, &c->sruns, &c->tile_runs, &c->tile_center, &c->tile_info, &c->tile_slots, &c->trows,
+                    &c->exch_holes, &c->ghost_src, &c->ghost_shift, &c->sruns, &c->tile_runs, &c->tile_center, &c->tile_info, &c->tile_slots, &c->trows,
                     &c->tnum};
   for (DevBuf* b : bufs) b->release();
   for (int w = 0; w < MMD_MAX_SWAPS; w++) c->sw[w].list.release();
@@ -1956,6 +1983,9 @@ int mmd_set_option(mmd_ctx* c, const char* key, long long value) {
     c->eam_tpa = (int)value;
   } else if (k == "tile_lists") {  // 1: tile-resident lists + shared-memory force kernels where they apply; 0: classic rows
     c->tile_enable = value != 0;  // takes effect at the next neighbor build
+  } else if (k == "fuse_halo") {
+    c->fuse_halo = value != 0;
+    if (!c->fuse_halo) c->ghosts_resolved = false;
   } else if (k == "tile_eam") {
     c->tile_eam = value != 0;
   } else if (k == "p2p_halo") {  // 0: forward halo through NCCL send/recv even when peer windows are mapped
