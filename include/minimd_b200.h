@@ -182,8 +182,7 @@ typedef struct {
   int step;
   double sum_mv2, eng_vdwl, virial;
 } mmd_thermo_sample;
-/* Runs params->ntimes steps entirely on the device (launch-only host loop, CUDA-graph'ed
- * where the step sequence repeats).  samples[max_samples] receives the thermo steps.
+/* Runs params->ntimes steps entirely on the device (launch-only host loop).  samples[max_samples] receives the thermo steps.
  * elapsed_ms (may be NULL): CUDA-event time of the loop on the context's stream. */
 int mmd_run(mmd_ctx* ctx, const mmd_run_params* params, mmd_thermo_sample* samples, int max_samples,
             int* nsamples, float* elapsed_ms);
@@ -200,7 +199,19 @@ int mmd_run_phase_times(mmd_ctx* ctx, double* ms, long long* calls, int reset);
 /* Named integer/real queries ("nlocal", "nghost", "maxneighs", "mbins", "total_neigh",
  * "neigh_builds", "nswap", ...); returns MMD_ERR_ARG for unknown keys. */
 int mmd_query_int(mmd_ctx* ctx, const char* key, long long* value);
-/* Tuning knobs ("lj_threads_per_atom", "use_graph", ...). */
+/* Run-time switches (all ranks must use the same values):
+ *   "tile_lists" (1)   neighbor lists as 16-bit tile-local rows + shared-memory force kernels (LJ); 0 = classic rows of
+ *                      global ids.  Takes effect at the next mmd_neigh_build.  mmd_neigh_download returns the reference's
+ *                      rows in either case.
+ *   "tile_eam" (0)     tile-resident lists for the EAM force too (measured slower than the classic kernels)
+ *   "fuse_integrate" (1)  mmd_run: finalIntegrate(n) + initialIntegrate(n+1) in one kernel
+ *   "fuse_force" (1)      mmd_run, tile lists: ... and both inside the force kernel's epilogue
+ *   "fuse_halo" (1)       one rank: forward halo in one launch (ghosts resolved to their local source)
+ *   "p2p_halo" (1)        several ranks: forward halo over CUDA-IPC peer windows; 0 = NCCL send/recv
+ *   "lj_threads_per_atom" (0 = auto), "eam_threads_per_atom" (8): lanes per atom of the classic kernels
+ *   "phase_timing" (0)    per-phase CUDA-event timing of mmd_run
+ * Queries added by these paths: "list_tile", "tile_ok", "tile_builds", "tile_fallbacks", "tile_max_halo",
+ * "tile_max_full", "tile_row_capacity", "tile_count", "p2p_active", "p2p_calls". */
 int mmd_set_option(mmd_ctx* ctx, const char* key, long long value);
 
 #ifdef __cplusplus
