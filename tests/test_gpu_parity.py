@@ -352,3 +352,38 @@ def test_time_loop_matches_oracle(force, half, gn, prec, tol, tile):
     if prec == "f64":
         assert c.query("total_neigh") == int(o.numneigh().sum())
         assert c.query("maxneighs") == o.geti("maxneighs")
+
+
+# ------------------------------------------------------------------------------------------
+# run-time switches: every optional fusion must reproduce the unfused path
+# ------------------------------------------------------------------------------------------
+def _run_with(options, prec="f64", steps=60):
+    cfg = Config(nx=8, ny=8, nz=8, ntimes=steps, halfneigh=1, ghost_newton=1, thermo_nstat=20)
+    o = Oracle(cfg, prec)
+    c = context_from_oracle(o)
+    for k, v in options.items():
+        c.set_option(k, v)
+    c.exchange()
+    c.borders()
+    c.build(1, 1, 100)
+    samples, _ = c.run(run_params(o, steps))
+    d = c.download("xv", count=c.counts()[0])
+    return samples, d["x"], d["v"], c.query("launches")
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_fused_paths_reproduce_the_unfused_ones(prec):
+    base = _run_with(dict(fuse_halo=0, fuse_force=0, fuse_integrate=0), prec)
+    # one-launch forward halo: an exact copy+shift either way
+    halo = _run_with(dict(fuse_halo=1, fuse_force=0, fuse_integrate=0), prec)
+    assert np.array_equal(halo[1], base[1]) and np.array_equal(halo[2], base[2])
+    assert halo[3] < base[3]
+    # Verlet halves in one kernel / in the force kernel's epilogue: same operations in the same order
+    for opts in (dict(fuse_halo=1, fuse_force=0, fuse_integrate=1), dict(fuse_halo=1, fuse_force=1, fuse_integrate=1)):
+        got = _run_with(opts, prec)
+        tol = 1e-12 if prec == "f64" else 1e-5
+        assert_close(got[1], base[1], tol, f"x {opts}")
+        assert_close(got[2], base[2], tol, f"v {opts}")
+        for (s0, m0, e0, v0), (s1, m1, e1, v1) in zip(base[0], got[0]):
+            assert s0 == s1 and abs(m0 - m1) <= tol * abs(m0) and abs(e0 - e1) <= tol * abs(e0)
+        assert got[3] < base[3]
