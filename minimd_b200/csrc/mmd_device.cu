@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -159,7 +160,9 @@ struct mmd_ctx {
   bool list_tile = false;   // format of the current list
   TileGeo tgeo;
   int nsruns = 0;           // runs of the symmetric (full) stencil
-  DevBuf sruns, tile_runs, tile_center, tile_info, tile_slots, trows, tnum;
+  DevBuf sruns, tile_runs, tile_center, tile_info, tile_slots, tile_oslot, trows, tnum;
+  bool tile_xsort = true;     // option "tile_xsort": x-sorted windows + interval build (neigh_build_tile3_kernel)
+  bool list_xsorted = false;  // the current list was built on x-sorted windows
   int tcap = 0;             // row capacity (16-bit entries, multiple of 8)
   int tcap_floor = 0;       // raised when a build overflowed its rows
   int tile_max_h = 0, tile_max_full = 0;
@@ -514,10 +517,23 @@ template <class T> struct Impl {
     LAUNCH(c, tile_table_kernel, div_up(g.ntiles, 4), 128, g, c->bin_start.as<int>(), c->bin_atoms.as<int>(), c->mbins,
            c->nlocal, c->tile_runs.as<int2>(), c->tile_center.as<int4>(), c->tile_info.as<int2>(), c->d_scal + 11,
            c->d_scal + 13);
-    CU(cudaMemcpyAsync(c->tile_slots.p, c->bin_atoms.p, (size_t)nall * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    // the windows' slot -> atom map: a private copy of the CSR bins, every bin sorted by x when the interval build is used
+    bool xsorted = c->tile_xsort && c->tile_build2 && c->nsruns <= 32;
+    if (xsorted) {
+      MM(c->tile_oslot.reserve((size_t)std::max(c->cap, nall) * sizeof(int), c->stream));
+      LAUNCH(c, bin_xsort_kernel<T>, div_up(c->mbins, TPB), TPB, c->x.as<V>(), c->bin_start.as<int>(), c->bin_atoms.as<int>(),
+             c->mbins, c->tile_slots.as<int>(), c->tile_oslot.as<int>(), c->d_scal + 12);
+    } else {
+      CU(cudaMemcpyAsync(c->tile_slots.p, c->bin_atoms.p, (size_t)nall * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    }
     const int mode = halfneigh ? (gn ? 1 : 2) : 0;
     // the largest halo window sizes the shared memory of the build and force kernels
     MM(read_status(c));
+    if (xsorted && (c->h_scal[12] & 8)) {  // a bin too full for the thread-local sort: windows stay in CSR order
+      xsorted = false;
+      CU(cudaMemsetAsync(c->d_scal + 12, 0, sizeof(int), c->stream));
+      CU(cudaMemcpyAsync(c->tile_slots.p, c->bin_atoms.p, (size_t)nall * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    }
     c->tile_max_h = c->h_scal[11];
     const int hcap_limit = (int)((227 * 1024 - 4096) / (3 * sizeof(T) + 1)) & ~63;
     if (c->tile_max_h > hcap_limit) {
@@ -533,6 +549,8 @@ template <class T> struct Impl {
       double cmax = cuts[0];
       for (double v : cuts) { if (v != cuts[0]) B.uniform_cut = 0; cmax = std::max(cmax, v); }
       B.band = (float)(1e-4 * cmax);
+      // culling radius: cutneigh + 0.1 % + 2 % of the smallest bin edge (covers the FP32 images and coord2bin's rounding)
+      B.rcull = (float)(std::sqrt(cmax) * 1.001 + 0.02 / std::max(std::max(c->geo.bininvx, c->geo.bininvy), c->geo.bininvz));
       B.binsize[0] = 1.0 / c->geo.bininvx; B.binsize[1] = 1.0 / c->geo.bininvy; B.binsize[2] = 1.0 / c->geo.bininvz;
       B.mbinlo[0] = c->geo.mbinxlo; B.mbinlo[1] = c->geo.mbinylo; B.mbinlo[2] = c->geo.mbinzlo;
     }
@@ -558,7 +576,35 @@ template <class T> struct Impl {
       c->cutneighsq.as<T>(), c->ntypes, g, B, c->tile_runs.as<int2>(), c->tile_center.as<int4>(), c->tile_info.as<int2>(),  \
       c->trows.as<unsigned short>(), c->tcap, c->numneigh.as<int>(), c->tnum.as<int2>(), c->d_scal + 12, c->d_scal + 1,    \
       c->d_scal + 10, c->d_total
-      if (use_b2) {
+      if (xsorted) {
+        const size_t b3_smem = build3_smem_bytes<T>(g, g.hcap, !B.uniform_cut);
+        static bool attr3_done = false;
+        const int smax = 227 * 1024 - 2048;
+        if (!attr3_done) {
+          CU(cudaFuncSetAttribute(neigh_build_tile3_kernel<T, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+          CU(cudaFuncSetAttribute(neigh_build_tile3_kernel<T, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+          CU(cudaFuncSetAttribute(neigh_build_tile3_kernel<T, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+          CU(cudaFuncSetAttribute(neigh_build_tile3_kernel<T, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+          CU(cudaFuncSetAttribute(neigh_build_tile3_kernel<T, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+          CU(cudaFuncSetAttribute(neigh_build_tile3_kernel<T, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+          attr3_done = true;
+        }
+#define NB3_ARGS                                                                                                          \
+  c->x.as<V>(), c->nlocal, c->bin_start.as<int>(), c->tile_slots.as<int>(), c->mbins, c->sruns.as<StencilRun>(), c->nsruns, \
+      c->cutneighsq.as<T>(), c->ntypes, g, B, c->tile_runs.as<int2>(), c->tile_center.as<int4>(), c->tile_info.as<int2>(),  \
+      c->trows.as<unsigned short>(), c->tcap, c->numneigh.as<int>(), c->tnum.as<int2>(), c->d_scal + 12, c->d_scal + 1,    \
+      c->d_scal + 10, c->d_total
+        if (B.uniform_cut) {
+          if (mode == 0) LAUNCH_SMEM(c, (neigh_build_tile3_kernel<T, 0, 1>), g.ntiles, TB2_THREADS, b3_smem, NB3_ARGS);
+          if (mode == 1) LAUNCH_SMEM(c, (neigh_build_tile3_kernel<T, 1, 1>), g.ntiles, TB2_THREADS, b3_smem, NB3_ARGS);
+          if (mode == 2) LAUNCH_SMEM(c, (neigh_build_tile3_kernel<T, 2, 1>), g.ntiles, TB2_THREADS, b3_smem, NB3_ARGS);
+        } else {
+          if (mode == 0) LAUNCH_SMEM(c, (neigh_build_tile3_kernel<T, 0, 0>), g.ntiles, TB2_THREADS, b3_smem, NB3_ARGS);
+          if (mode == 1) LAUNCH_SMEM(c, (neigh_build_tile3_kernel<T, 1, 0>), g.ntiles, TB2_THREADS, b3_smem, NB3_ARGS);
+          if (mode == 2) LAUNCH_SMEM(c, (neigh_build_tile3_kernel<T, 2, 0>), g.ntiles, TB2_THREADS, b3_smem, NB3_ARGS);
+        }
+#undef NB3_ARGS
+      } else if (use_b2) {
         static bool attr_done = false;
         const int smax = 227 * 1024 - 2048;
         if (!attr_done) {
@@ -608,6 +654,7 @@ template <class T> struct Impl {
     }
     c->neigh_stride = (c->maxneighs + 7) & ~7;
     c->list_tile = true;
+    c->list_xsorted = xsorted;
     c->tile_builds++;
     *done = true;
     return MMD_OK;
@@ -618,9 +665,14 @@ template <class T> struct Impl {
     if (!c->list_tile) return MMD_OK;
     const TileGeo& g = c->tgeo;
     MM(c->neighbors.reserve((size_t)std::max(c->nlocal, 1) * c->neigh_stride * sizeof(int), c->stream, 0, 1.05));
+    CU(cudaMemsetAsync(c->d_scal + 12, 0, sizeof(int), c->stream));
     LAUNCH(c, tile_rows_export_kernel, g.ntiles, TILE_THREADS, g, c->tile_runs.as<int2>(), c->tile_center.as<int4>(),
-           c->tile_info.as<int2>(), c->tile_slots.as<int>(), c->trows.as<unsigned short>(), c->tnum.as<int2>(), c->tcap,
-           c->nlocal, c->list_half ? 1 : 0, c->neighbors.as<int>(), c->neigh_stride, c->neigh_stride);
+           c->tile_info.as<int2>(), c->tile_slots.as<int>(), c->list_xsorted ? c->tile_oslot.as<int>() : (const int*)nullptr,
+           c->trows.as<unsigned short>(), c->tnum.as<int2>(), c->tcap, c->nlocal, c->list_half ? 1 : 0,
+           c->neighbors.as<int>(), c->neigh_stride, c->neigh_stride, c->d_scal + 12);
+    CU(cudaMemcpyAsync(c->h_scal + 12, c->d_scal + 12, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->h_scal[12] & 16) return set_err(MMD_ERR_STATE, "neighbor export: a row is longer than the sorting export handles");
     return MMD_OK;
   }
   // switch the current list to the classic format (kernels without a tile variant)
@@ -1502,7 +1554,7 @@ int mmd_ctx_destroy(mmd_ctx* c) {
                     &c->tile_sums, &c->numneigh, &c->neighbors, &c->lj_cut, &c->lj_s6, &c->lj_eps, &c->eam_rho_val,
                     &c->eam_rho_der, &c->eam_z2_val, &c->eam_z2_der, &c->eam_frho_val, &c->eam_frho_der, &c->eam_cut,
                     &c->rho, &c->fp, &c->border_tiles, &c->sendbuf, &c->recvbuf, &c->exch_flag, &c->exch_pos,
-                    &c->exch_holes, &c->ghost_src, &c->ghost_shift, &c->sruns, &c->tile_runs, &c->tile_center, &c->tile_info, &c->tile_slots, &c->trows,
+                    &c->exch_holes, &c->ghost_src, &c->ghost_shift, &c->sruns, &c->tile_runs, &c->tile_center, &c->tile_info, &c->tile_slots, &c->tile_oslot, &c->trows,
                     &c->tnum};
   for (DevBuf* b : bufs) b->release();
   for (int w = 0; w < MMD_MAX_SWAPS; w++) c->sw[w].list.release();
@@ -1957,6 +2009,7 @@ int mmd_query_int(mmd_ctx* c, const char* key, long long* value) {
   else if (k == "nranks") *value = c->nranks;
   else if (k == "p2p_active") *value = c->p2p_on;
   else if (k == "p2p_calls") *value = c->p2p_calls;
+  else if (k == "list_xsorted") *value = c->list_xsorted;
   else if (k == "tile_lists") *value = c->tile_enable;
   else if (k == "fuse_force") *value = c->fuse_force && c->fuse_integrate;
   else if (k == "list_tile") *value = c->list_tile;
@@ -1986,6 +2039,8 @@ int mmd_set_option(mmd_ctx* c, const char* key, long long value) {
   } else if (k == "fuse_halo") {
     c->fuse_halo = value != 0;
     if (!c->fuse_halo) c->ghosts_resolved = false;
+  } else if (k == "tile_xsort") {
+    c->tile_xsort = value != 0;
   } else if (k == "tile_eam") {
     c->tile_eam = value != 0;
   } else if (k == "p2p_halo") {  // 0: forward halo through NCCL send/recv even when peer windows are mapped

@@ -317,6 +317,7 @@ constexpr int TB2_THREADS = 256, TB2_WARPS = TB2_THREADS / 32;  // each warp tak
 template <class T> struct Build2Params {
   T cut0;         // cutneighsq when all type pairs share it
   float band;     // FP64 build: |rsq32 - cut| <= band -> exact FP64 test
+  float rcull;    // sqrt(max cutneighsq) plus a safety margin: the half-width of an atom's candidate interval derives from it
   double binsize[3];
   int mbinlo[3];
   int uniform_cut;
@@ -680,6 +681,307 @@ neigh_build_tile2_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* _
 }
 
 // ---------------------------------------------------------------------------------------
+// x-sorted windows.  The slot -> atom map the tile kernels stage from is a private copy of the CSR bins; inside every
+// bin it may be put in any order, because tile-local indices only have to agree between the build and the force
+// kernels.  Sorting each bin by x makes every pencil run of a halo window ascending in x (bins ascend along the run),
+// so the candidates of an atom in a pencil are ONE interval [x_i - xr, x_i + xr] found by two binary searches:
+// the build then tests ~140 candidates per atom instead of the ~575 of the bin stencil.  oslot keeps the original
+// CSR position of every entry: the export sorts rows by it, which restores the reference's row order.
+// status |= 8 when a bin is too full for the thread-local sort (the caller then builds without x-sorted windows).
+// ---------------------------------------------------------------------------------------
+template <bool V> struct TileTag { static constexpr bool value = V; };
+constexpr int XSORT_MAX = 48;
+template <class T>
+__global__ void bin_xsort_kernel(const Vec4<T>* __restrict__ x, const int* __restrict__ bin_start,
+                                 const int* __restrict__ bin_atoms, int mbins, int* __restrict__ slots,
+                                 int* __restrict__ oslot, int* __restrict__ status) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= mbins) return;
+  const int s0 = bin_start[b], n = bin_start[b + 1] - s0;
+  if (n <= 0) return;
+  if (n > XSORT_MAX) {
+    atomicOr(status, 8);
+    for (int k = 0; k < n; k++) { slots[s0 + k] = bin_atoms[s0 + k]; oslot[s0 + k] = s0 + k; }
+    return;
+  }
+  T key[XSORT_MAX];
+  int id[XSORT_MAX], os[XSORT_MAX];
+  for (int k = 0; k < n; k++) {
+    const int a = bin_atoms[s0 + k];
+    const T xa = x[a].x;
+    int j = k - 1;
+    while (j >= 0 && key[j] > xa) {  // stable: equal keys keep their id order
+      key[j + 1] = key[j]; id[j + 1] = id[j]; os[j + 1] = os[j];
+      j--;
+    }
+    key[j + 1] = xa; id[j + 1] = a; os[j + 1] = s0 + k;
+  }
+  for (int k = 0; k < n; k++) { slots[s0 + k] = id[k]; oslot[s0 + k] = os[k]; }
+}
+
+// ---------------------------------------------------------------------------------------
+// Neighbor build on x-sorted windows: one CTA per tile, one warp per centre pencil, one atom at a time.
+// Lane r owns stencil run r (<= 32 runs): it turns the run's bins into the index interval of this atom's candidates
+// (slab distance in y/z leaves an x half-width xr; two binary searches over the run's staged x).  The non-empty
+// intervals are compacted and their prefix sums kept in shared memory; a sweep of 32 candidates finds its interval
+// with one REDUX.OR + POPC.  Distance test, guard band, exact FP64 re-test, half-list flag, counters and row layout
+// are those of neigh_build_tile2_kernel; rows come out in candidate order (ascending tile-local index).
+// ---------------------------------------------------------------------------------------
+template <class T> __host__ __device__ inline size_t build3_smem_bytes(const TileGeo& g, int hcap, bool with_types) {
+  return (size_t)hcap * 3 * sizeof(float) + (with_types ? (size_t)hcap : 0) + (size_t)g.nrun * (TBX + 2 * g.sx + 1) * sizeof(int) +
+         (size_t)TB2_WARPS * 32 * sizeof(int4) + (2 * TILE_MAXRUN + 1) * sizeof(int) + 96;
+}
+
+template <class T, int MODE, int UC>
+__global__ void __launch_bounds__(TB2_THREADS, 3)
+neigh_build_tile3_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* __restrict__ bin_start,
+                         const int* __restrict__ slots, int mbins, const StencilRun* __restrict__ sruns, int nsr,
+                         const T* __restrict__ cutneighsq, int ntypes, TileGeo g, Build2Params<T> B,
+                         const int2* __restrict__ tile_runs, const int4* __restrict__ tile_center,
+                         const int2* __restrict__ tile_info, unsigned short* __restrict__ rows, int tcap,
+                         int* __restrict__ numneigh_half, int2* __restrict__ row_atom, int* __restrict__ status,
+                         int* __restrict__ max_half, int* __restrict__ max_full, unsigned long long* __restrict__ total_half) {
+  extern __shared__ __align__(16) unsigned char b3_smem[];
+  const int t = blockIdx.x;
+  const int2 inf = tile_info[t];
+  if (inf.y == 0) return;
+  const int H = inf.x;
+  const int WX1 = TBX + 2 * g.sx + 1;
+  float* sx = reinterpret_cast<float*>(b3_smem);
+  float* sy = sx + g.hcap;
+  float* sz = sy + g.hcap;
+  // [warps][32] dense intervals of the current atom: {first index - prefix, prefix of lengths, class | slot0*4, -}
+  // (directly behind the coordinate arrays: hcap is a multiple of 64, so the records are 16-byte aligned)
+  int4* s_dense = reinterpret_cast<int4*>(sz + g.hcap);
+  int* s_binoff = reinterpret_cast<int*>(s_dense + TB2_WARPS * 32);   // [nrun][WX1] tile-local start index of each window bin
+  int* s_run_start = s_binoff + g.nrun * WX1;                         // [nrun]
+  int* s_run_off = s_run_start + TILE_MAXRUN;             // [nrun+1]
+  unsigned char* st = reinterpret_cast<unsigned char*>(s_run_off + TILE_MAXRUN + 1);  // [hcap] types (!UC)
+
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int tx = t % g.ntx, ty = (t / g.ntx) % g.nty, tz = t / (g.ntx * g.nty);
+  const int bx0 = tx * TBX - g.ox, by0 = ty * TBY - g.oy, bz0 = tz * TBZ - g.oz;
+  const int xlo = max(0, bx0 - g.sx), xhi = min(g.mbx, bx0 + TBX + g.sx);
+  const T org_x = sizeof(T) == 8 ? (T)((bx0 - g.sx + B.mbinlo[0]) * B.binsize[0]) : (T)0;
+  const T org_y = sizeof(T) == 8 ? (T)((by0 - g.sy + B.mbinlo[1]) * B.binsize[1]) : (T)0;
+  const T org_z = sizeof(T) == 8 ? (T)((bz0 - g.sz + B.mbinlo[2]) * B.binsize[2]) : (T)0;
+
+  const int2* tr = tile_runs + (size_t)t * g.nrun;
+  for (int p = threadIdx.x; p < g.nrun; p += blockDim.x) {
+    const int2 r = tr[p];
+    s_run_start[p] = r.x;
+    s_run_off[p] = r.y;
+  }
+  if (threadIdx.x == 0) s_run_off[g.nrun] = H;
+  __syncthreads();
+  for (int e = threadIdx.x; e < g.nrun * WX1; e += blockDim.x) {
+    const int p = e / WX1, wx = e - p * WX1;
+    const int y = by0 - g.sy + p % g.nry, z = bz0 - g.sz + p / g.nry;
+    int v = s_run_off[p + 1];
+    if (y >= 0 && y < g.mby && z >= 0 && z < g.mbz && xlo + wx < xhi)
+      v = s_run_off[p] + (bin_start[min(tile_bin_id(g, xlo + wx, y, z), mbins)] - s_run_start[p]);
+    s_binoff[e] = v;
+  }
+  for (int p = w; p < g.nrun; p += nw) {
+    const int start = s_run_start[p], off = s_run_off[p], len = s_run_off[p + 1] - off;
+    for (int k = lane; k < len; k += 32) {
+      const int id = __ldg(slots + start + k);
+      const Vec4<T> v = ldg4(x + id);
+      sx[off + k] = (float)(v.x - org_x);
+      sy[off + k] = (float)(v.y - org_y);
+      sz[off + k] = (float)(v.z - org_z);
+      if (!UC) st[off + k] = (unsigned char)lane_to_type(v.w);
+    }
+  }
+  __syncthreads();
+
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int4* dense = s_dense + w * 32;
+  const float bsy = (float)B.binsize[1], bsz = (float)B.binsize[2];
+  const float ey0 = (float)((by0 - g.sy + B.mbinlo[1]) * B.binsize[1] - (double)org_y);
+  const float ez0 = (float)((bz0 - g.sz + B.mbinlo[2]) * B.binsize[2] - (double)org_z);
+  const float rc = B.rcull, rc2 = rc * rc, fcut0 = (float)B.cut0, band = B.band;
+  int warp_max_h = 0, warp_max_f = 0;
+  unsigned long long warp_total = 0ull;
+
+  for (int cr = w; cr < TILE_NCENTER; cr += nw) {
+    const int cy = cr % TBY, cz = cr / TBY;
+    const int by = by0 + cy, bz = bz0 + cz;
+    if (by < 0 || by >= g.mby || bz < 0 || bz >= g.mbz) continue;
+    const int4 ce = tile_center[(size_t)t * TILE_NCENTER + cr];
+    const int pc = (cy + g.sy) + (cz + g.sz) * g.nry;
+    const int slot0_c = s_run_start[pc] - s_run_off[pc];
+    const float ey_own = ey0 + (float)(cy + g.sy) * bsy, ez_own = ez0 + (float)(cz + g.sz) * bsz;
+    for (int cx = 0; cx < TBX; cx++) {
+      const int bx = bx0 + cx;
+      if (bx < 0 || bx >= g.mbx) continue;
+      const int xw = bx - xlo;
+      const int own_lo = s_binoff[pc * WX1 + xw], own_hi = s_binoff[pc * WX1 + xw + 1];
+      if (own_hi == own_lo) continue;
+      // ---- lane r: stencil run r of this bin (which window bins it covers, its pencil) ----
+      int r_row = 0, r_wlo = 0, r_whi = -1, r_info = 0, r_slot0 = 0;
+      float r_ylo = 0.f, r_zlo = 0.f;
+      if (lane < nsr) {
+        const StencilRun run = sruns[lane];
+        const int dxlo = run.off - (run.dz * g.mby + run.dy) * g.mbx;
+        const int yy = by + run.dy, zz = bz + run.dz;
+        const int wlo = xw + dxlo, whi = wlo + run.len;
+        if (yy < 0 || yy >= g.mby || zz < 0 || zz >= g.mbz || wlo < 0 || xlo + whi > xhi) {
+          // only matters if the bin owns local atoms (checked per atom below)
+          r_whi = -2;
+        } else {
+          const int p = (cy + g.sy + run.dy) + (cz + g.sz + run.dz) * g.nry;
+          r_row = p * WX1; r_wlo = wlo; r_whi = whi;
+          r_ylo = ey_own + (float)run.dy * bsy;
+          r_zlo = ez_own + (float)run.dz * bsz;
+          r_slot0 = s_run_start[p] - s_run_off[p];
+          const bool upper = run.dz > 0 || (run.dz == 0 && run.dy > 0);
+          const bool ownp = run.dz == 0 && run.dy == 0;
+          r_info = (upper ? 2 : 0) | (ownp ? 1 : 0);
+        }
+      }
+      const bool bad_geom = __any_sync(0xffffffffu, r_whi == -2);
+
+      for (int a = own_lo; a < own_hi; a++) {
+        const int id_i = __ldg(slots + slot0_c + a);
+        if (id_i >= nlocal) continue;  // warp-uniform
+        if (bad_geom) { if (lane == 0) atomicOr(status, 2); continue; }
+        const float xi = sx[a], yi = sy[a], zi = sz[a];
+        const int ti = UC ? 0 : (int)st[a];
+        const int q = ce.z + (a - ce.x);
+        unsigned short* rowp = rows + (size_t)q * tcap;
+
+        // ---- this atom's candidate interval in every run ----
+        int L = 0, len = 0;
+        if (lane < nsr && r_whi >= 0) {
+          const float gy = fmaxf(0.0f, fmaxf(r_ylo - yi, yi - (r_ylo + bsy)));
+          const float gz = fmaxf(0.0f, fmaxf(r_zlo - zi, zi - (r_zlo + bsz)));
+          const float rem = rc2 - gy * gy - gz * gz;
+          if (rem > 0.0f) {
+            const float xr = sqrtf(rem);
+            const int lo_i = s_binoff[r_row + r_wlo], hi_i = s_binoff[r_row + r_whi];
+            const float xa = xi - xr, xb = xi + xr;
+            int l0 = lo_i, l1 = hi_i;  // first index with sx >= xa
+            while (l0 < l1) {
+              const int mid = (l0 + l1) >> 1;
+              if (sx[mid] < xa) l0 = mid + 1; else l1 = mid;
+            }
+            L = l0;
+            l1 = hi_i;                  // first index with sx > xb
+            while (l0 < l1) {
+              const int mid = (l0 + l1) >> 1;
+              if (sx[mid] <= xb) l0 = mid + 1; else l1 = mid;
+            }
+            len = l0 - L;
+          }
+        }
+        const unsigned nz = __ballot_sync(0xffffffffu, len > 0);
+        const int nd = __popc(nz);
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const int M = __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
+        if (len > 0)  // flags in the two low bits of .z, CSR slot of tile-local index 0 above them
+          dense[__popc(nz & lt_mask)] = make_int4(L - (incl - len), incl - len, r_slot0 * 4 + r_info, 0);
+        __syncwarp();
+        const int my_dpref = lane < nd ? dense[lane].y : 0x7fffffff;
+
+        int n_t = 0, h_t = 0;
+        // one pass over the atom's candidates, 32 per sweep; EXACT adds the FP64 re-test of candidates inside the guard band
+        auto sweep_all = [&](auto exact_tag) -> bool {
+          constexpr bool EXACT = decltype(exact_tag)::value;
+          n_t = 0; h_t = 0;
+          bool closeany = false;
+          const unsigned own_n = (unsigned)(own_hi - own_lo);
+          for (int s0 = 0; s0 < M; s0 += 32) {
+            const int n = s0 + lane;
+            const bool valid = n < M;
+            const bool starts_here = my_dpref >= s0 && my_dpref < s0 + 32;
+            const unsigned starts = __reduce_or_sync(0xffffffffu, starts_here ? (1u << (my_dpref - s0)) : 0u);
+            const int before = __popc(__ballot_sync(0xffffffffu, my_dpref < s0));
+            const int rr = valid ? before + __popc(starts & ((2u << lane) - 1u)) - 1 : 0;
+            const int4 dv = dense[rr];
+            const int lc = valid ? dv.x + n : a;
+            const int info = dv.z;
+            const float dx = xi - sx[lc], dy = yi - sy[lc], dz = zi - sz[lc];
+            T cut = B.cut0;
+            float fc = fcut0;
+            if (!UC) { cut = __ldg(&cutneighsq[ti * ntypes + (int)st[lc]]); fc = (float)cut; }
+            bool ok;
+            if (sizeof(T) == 4) {
+              ok = rsq_unfused(dx, dy, dz) <= fc;
+            } else {
+              const float d = (dx * dx + dy * dy + dz * dz) - fc;
+              ok = d < -band;
+              const bool close = fabsf(d) <= band && lc != a;
+              if (!EXACT) closeany = closeany || close;
+              if (EXACT) {
+                if (__any_sync(0xffffffffu, close && valid)) {
+                  if (close && valid) ok = build2_exact_within<T>(x, id_i, __ldg(slots + (info >> 2) + lc), cut);
+                }
+              }
+            }
+            ok = ok && valid && lc != a;
+            bool half = true;
+            if (MODE == 1) {
+              const bool own_bin = (info & 1) && (unsigned)(lc - own_lo) < own_n;
+              half = (info & 2) != 0 || ((info & 1) && lc >= own_hi);
+              if (__any_sync(0xffffffffu, own_bin && ok)) {  // within the bin the reference orders by atom id
+                if (own_bin && ok) {
+                  const int id_j = __ldg(slots + slot0_c + lc);
+                  half = id_j > id_i;
+                  if (half && id_j >= nlocal) half = !build2_ghost_below<T>(x, id_i, id_j);
+                }
+              }
+            }
+            if (MODE == 2) {
+              half = false;
+              if (ok) half = __ldg(slots + (info >> 2) + lc) > id_i;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            const unsigned mh = MODE == 0 ? m : __ballot_sync(0xffffffffu, ok && half);
+            if (ok) {
+              const int pos = n_t + __popc(m & lt_mask);
+              if (pos < tcap) rowp[pos] = (unsigned short)(lc | ((MODE != 0 && half) ? TILE_HALF_BIT : 0));
+            }
+            n_t += __popc(m);
+            h_t += __popc(mh);
+          }
+          return __any_sync(0xffffffffu, closeany);
+        };
+        if (sizeof(T) == 4) {
+          sweep_all(TileTag<false>());
+        } else if (sweep_all(TileTag<false>())) {
+          sweep_all(TileTag<true>());  // a candidate sat inside the guard band: redo this atom with exact FP64 tests
+        }
+        if (lane == 0) {
+          numneigh_half[id_i] = h_t;
+          row_atom[q] = make_int2(id_i, n_t);
+        }
+        warp_max_h = max(warp_max_h, h_t);
+        warp_max_f = max(warp_max_f, n_t);
+        if (lane == 0) warp_total += (unsigned long long)h_t;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    warp_max_h = max(warp_max_h, __shfl_xor_sync(0xffffffffu, warp_max_h, o));
+    warp_max_f = max(warp_max_f, __shfl_xor_sync(0xffffffffu, warp_max_f, o));
+    warp_total += __shfl_xor_sync(0xffffffffu, warp_total, o);
+  }
+  if (lane == 0) {
+    atomicMax(max_half, warp_max_h);
+    atomicMax(max_full, warp_max_f);
+    atomicAdd(total_half, warp_total);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Shared-memory image of a tile: run tables + SoA positions of the halo window.
 // ---------------------------------------------------------------------------------------
 template <class T> struct TileSmem {
@@ -943,11 +1245,12 @@ force_lj_tile_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Til
 // Export to the reference's row format (Neighbor::neighbors / numneigh): global atom ids, the
 // half-list subset when the list was built for half neighbor semantics.  One CTA per tile.
 // ---------------------------------------------------------------------------------------
+constexpr int TILE_EXPORT_MAX = 224;  // longest row the sorting export handles
 __global__ void __launch_bounds__(TILE_THREADS)
 tile_rows_export_kernel(TileGeo g, const int2* __restrict__ tile_runs, const int4* __restrict__ tile_center,
-                        const int2* __restrict__ tile_info, const int* __restrict__ slots,
+                        const int2* __restrict__ tile_info, const int* __restrict__ slots, const int* __restrict__ oslot,
                         const unsigned short* __restrict__ rows, const int2* __restrict__ row_atom, int tcap, int nlocal,
-                        int half_only, int* __restrict__ out, int out_stride, int out_cap) {
+                        int half_only, int* __restrict__ out, int out_stride, int out_cap, int* __restrict__ status) {
   __shared__ int s_start[TILE_MAXRUN];
   __shared__ int s_off[TILE_MAXRUN + 1];
   const int t = blockIdx.x;
@@ -970,17 +1273,36 @@ tile_rows_export_kernel(TileGeo g, const int2* __restrict__ tile_runs, const int
       const int id = ta.x, cnt = ta.y;
       const unsigned short* row = rows + q * tcap;
       int n = 0, p = 0;
+      if (oslot == nullptr) {  // windows in CSR order: rows already are in the reference's order
+        for (int k = 0; k < cnt; k++) {
+          const unsigned short e = row[k];
+          if (half_only && !(e & TILE_HALF_BIT)) continue;
+          const int loc = e & 0x7fff;
+          if (loc < s_off[p]) p = 0;
+          while (p + 1 < g.nrun && loc >= s_off[p + 1]) p++;
+          const int j = slots[s_start[p] + (loc - s_off[p])];
+          if (n < out_cap) out[(size_t)id * out_stride + n] = j;
+          n++;
+        }
+        continue;
+      }
+      // x-sorted windows: the reference's row order is the order of the original CSR positions
+      int key[TILE_EXPORT_MAX], val[TILE_EXPORT_MAX];
       for (int k = 0; k < cnt; k++) {
         const unsigned short e = row[k];
         if (half_only && !(e & TILE_HALF_BIT)) continue;
         const int loc = e & 0x7fff;
-        // rows are not monotone across stencil pencils: restart the run search when needed
         if (loc < s_off[p]) p = 0;
         while (p + 1 < g.nrun && loc >= s_off[p + 1]) p++;
-        const int j = slots[s_start[p] + (loc - s_off[p])];
-        if (n < out_cap) out[(size_t)id * out_stride + n] = j;
+        const int sl = s_start[p] + (loc - s_off[p]);
+        if (n >= TILE_EXPORT_MAX) { atomicOr(status, 16); break; }
+        const int kk = oslot[sl], vv = slots[sl];
+        int j = n - 1;
+        while (j >= 0 && key[j] > kk) { key[j + 1] = key[j]; val[j + 1] = val[j]; j--; }
+        key[j + 1] = kk; val[j + 1] = vv;
         n++;
       }
+      for (int k = 0; k < n && k < out_cap; k++) out[(size_t)id * out_stride + k] = val[k];
     }
   }
 }
