@@ -733,7 +733,7 @@ template <class T> __host__ __device__ inline size_t build3_smem_bytes(const Til
 }
 
 template <class T, int MODE, int UC>
-__global__ void __launch_bounds__(TB2_THREADS, 3)
+__global__ void __launch_bounds__(TB2_THREADS, 4)
 neigh_build_tile3_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* __restrict__ bin_start,
                          const int* __restrict__ slots, int mbins, const StencilRun* __restrict__ sruns, int nsr,
                          const T* __restrict__ cutneighsq, int ntypes, TileGeo g, Build2Params<T> B,
