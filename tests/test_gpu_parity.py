@@ -51,15 +51,18 @@ CASES = [
 # ------------------------------------------------------------------------------------------
 # binning / borders / neighbor build / sort : bit-exact
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("tile", [1, 0])
+@pytest.mark.parametrize("tile", [1, 2, 0])
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 @pytest.mark.parametrize("steps", [0, 40])
 @pytest.mark.parametrize("case", range(len(CASES)))
 def test_borders_bins_and_lists_are_bit_exact(case, steps, prec, tile):
-    """tile=1: tile-resident 16-bit rows exported back to the reference's format; tile=0: classic rows."""
+    """tile=1: tile-resident 16-bit rows built on x-sorted windows (interval build) and exported back to the
+    reference's format; tile=2: the same rows from the per-bin candidate-table build (windows in CSR order);
+    tile=0: classic rows."""
     o = melted(CASES[case], steps, prec)
     c = context_from_oracle(o)
-    c.set_option("tile_lists", tile)
+    c.set_option("tile_lists", 1 if tile else 0)
+    c.set_option("tile_xsort", 1 if tile == 1 else 0)
     c.exchange()
     c.borders()
     # ghosts: counts, send lists, positions (+- prd shifts) and types
@@ -84,7 +87,8 @@ def test_borders_bins_and_lists_are_bit_exact(case, steps, prec, tile):
     # neighbor lists
     half, gn = o.geti("halfneigh"), o.geti("ghost_newton")
     mxn, total = c.build(half, gn, 100)
-    assert c.query("list_tile") == tile
+    assert c.query("list_tile") == (1 if tile else 0)
+    assert c.query("list_xsorted") == (1 if tile == 1 else 0)
     num, nb = c.neigh_download()
     onum, onb = o.numneigh(), o.neighbors()
     assert mxn == o.geti("maxneighs")
@@ -168,7 +172,11 @@ def test_lj_tile_force_energy_virial(half, gn, size, prec):
     """Tile-resident lists: every local atom's force is complete after the kernel (no scatter, no reverse
     halo), so half+ghost_newton is compared with the oracle AFTER its reverse_communicate."""
     o = melted(dict(nx=size[0], ny=size[1], nz=size[2], halfneigh=half, ghost_newton=gn), 40, prec)
-    c = setup_lists(o, tile=1)
+    c = context_from_oracle(o)
+    c.set_option("tile_xsort", 1 if size[0] == 8 else 0)   # one size per build flavour
+    c.exchange()
+    c.borders()
+    c.build(half, gn, 100)
     assert c.query("list_tile") == 1
     o.seti("evflag", 1)
     o.call("force_compute")
