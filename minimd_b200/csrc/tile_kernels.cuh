@@ -984,6 +984,8 @@ neigh_build_tile3_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* _
 // ---------------------------------------------------------------------------------------
 // Shared-memory image of a tile: run tables + SoA positions of the halo window.
 // ---------------------------------------------------------------------------------------
+template <class T> struct alignas(2 * sizeof(T)) Vec2 { T x, y; };
+
 template <class T> struct TileSmem {
   int* run_start;   // [nrun]
   int* run_off;     // [nrun + 1]
@@ -1005,7 +1007,8 @@ template <class T> __host__ __device__ inline size_t tile_smem_bytes(int hcap, b
 }
 
 // load run tables and stage the positions of the whole halo window (coalesced over CSR slots)
-template <class T, bool TYPES>
+// PACKXY: x and y of an atom share one 2-lane record in the [sx, sx + 2*hcap) region (one LDS.128 / LDS.64 fetches both)
+template <class T, bool TYPES, bool PACKXY = false>
 __device__ __forceinline__ int tile_stage(TileSmem<T>& S, const TileGeo& g, int t, int h, const int2* __restrict__ tile_runs,
                                           const int* __restrict__ slots, const Vec4<T>* __restrict__ x) {
   const int2* tr = tile_runs + (size_t)t * g.nrun;
@@ -1022,8 +1025,14 @@ __device__ __forceinline__ int tile_stage(TileSmem<T>& S, const TileGeo& g, int 
     for (int k = lane; k < len; k += 32) {
       const int id = __ldg(slots + start + k);
       const Vec4<T> v = ldg4(x + id);
-      S.sx[off + k] = v.x;
-      S.sy[off + k] = v.y;
+      if (PACKXY) {
+        Vec2<T> xy;
+        xy.x = v.x; xy.y = v.y;
+        reinterpret_cast<Vec2<T>*>(S.sx)[off + k] = xy;
+      } else {
+        S.sx[off + k] = v.x;
+        S.sy[off + k] = v.y;
+      }
       S.sz[off + k] = v.z;
       if (TYPES) S.st[off + k] = (unsigned char)lane_to_type(v.w);
     }
@@ -1112,7 +1121,8 @@ force_lj_tile_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Til
 
   TileSmem<T> S;
   S.carve(tile_smem_raw, g.hcap, !UNIFORM);
-  tile_stage<T, !UNIFORM>(S, g, t, inf.x, tile_runs, slots, x);
+  tile_stage<T, !UNIFORM, true>(S, g, t, inf.x, tile_runs, slots, x);
+  const Vec2<T>* __restrict__ sxy = reinterpret_cast<const Vec2<T>*>(S.sx);
 
   double eng = 0.0, vir = 0.0, ke = 0.0;
   for (; cr < TILE_NCENTER; cr += nw) {
@@ -1143,7 +1153,8 @@ force_lj_tile_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Til
           c_n = ldg_row8(rows + q * tcap + sub * 8);
         }
       }
-      const T xi = S.sx[aa], yi = S.sy[aa], zi = S.sz[aa];
+      const Vec2<T> xyi = sxy[aa];
+      const T xi = xyi.x, yi = xyi.y, zi = S.sz[aa];
       const int ti = UNIFORM ? 0 : (int)S.st[aa];
       T fx = 0, fy = 0, fz = 0;
       const int nch = (cnt + 7) >> 3;
@@ -1169,8 +1180,9 @@ force_lj_tile_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Til
           }
 #pragma unroll
           for (int e = 0; e < 4; e++) {
-            dx[e] = xi - S.sx[lj[e]];
-            dy[e] = yi - S.sy[lj[e]];
+            const Vec2<T> xyj = sxy[lj[e]];
+            dx[e] = xi - xyj.x;
+            dy[e] = yi - xyj.y;
             dz[e] = zi - S.sz[lj[e]];
           }
 #pragma unroll
