@@ -10,12 +10,13 @@
 // TBX x TBY x TBZ bins.  A tile's *halo window* is the tile grown by the stencil extent in every
 // direction; because atoms are held in bin order (CSR: bin_start/bin_atoms), each (y,z) pencil of the
 // window is ONE contiguous range of CSR slots -- a "run".  A tile-local index is the position of a
-// slot in the concatenation of the tile's runs.  For every local atom the list stores, in the
-// reference's row order (stencil order, then bin order: ref/neighbor.cpp:141-183), ALL neighbors
-// within cutneigh as 16-bit tile-local indices; bit 15 marks the entries that belong to the
-// reference's half list (ref/neighbor.cpp:154-171), so the reference's rows, numneigh and totals are
-// recovered exactly (tile_rows_export_kernel) while the force kernels evaluate every atom's complete
-// neighborhood ("owner computes"): no scatter to f[j], no reverse halo, no clearing of f.
+// slot in the concatenation of the tile's runs (the slot -> atom map is a private copy of the CSR bins,
+// each bin sorted by x for the interval build below).  For every local atom the list stores ALL neighbors
+// within cutneigh as 16-bit tile-local indices, in ascending order; bit 15 marks the entries that belong
+// to the reference's half list (ref/neighbor.cpp:154-171).  The reference's rows, numneigh and totals are
+// recovered exactly (tile_rows_export_kernel orders a row by the entries' original CSR position, which is
+// the reference's stencil-then-bin order, ref/neighbor.cpp:141-183) while the force kernels evaluate every
+// atom's complete neighborhood ("owner computes"): no scatter to f[j], no reverse halo, no clearing of f.
 // The pair set is identical to the reference's (each half-list pair appears in both owners' rows), so
 // forces, energies and virials agree with ForceLJ::compute_halfneigh / _fullneigh up to summation
 // order (ref/force_lj.cpp:185-263, :366-449).
