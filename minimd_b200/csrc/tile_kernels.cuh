@@ -1258,7 +1258,7 @@ force_lj_tile_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Til
 // Export to the reference's row format (Neighbor::neighbors / numneigh): global atom ids, the
 // half-list subset when the list was built for half neighbor semantics.  One CTA per tile.
 // ---------------------------------------------------------------------------------------
-constexpr int TILE_EXPORT_MAX = 224;  // longest row the sorting export handles
+constexpr int TILE_EXPORT_MAX = 512;  // longest row the sorting export handles
 __global__ void __launch_bounds__(TILE_THREADS)
 tile_rows_export_kernel(TileGeo g, const int2* __restrict__ tile_runs, const int4* __restrict__ tile_center,
                         const int2* __restrict__ tile_info, const int* __restrict__ slots, const int* __restrict__ oslot,

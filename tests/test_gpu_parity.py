@@ -395,3 +395,44 @@ def test_fused_paths_reproduce_the_unfused_ones(prec):
         for (s0, m0, e0, v0), (s1, m1, e1, v1) in zip(base[0], got[0]):
             assert s0 == s1 and abs(m0 - m1) <= tol * abs(m0) and abs(e0 - e1) <= tol * abs(e0)
         assert got[3] < base[3]
+
+
+# ------------------------------------------------------------------------------------------
+# geometries off the beaten path: wider stencils, fat and thin bins -- whichever list format the
+# library picks (tile rows from either build, or the classic fallback) must stay exact
+# ------------------------------------------------------------------------------------------
+ODD_CASES = [
+    dict(nx=8, ny=8, nz=8, force_cut=4.0),                 # stencil 7x7x7: 49 runs -> per-bin table build, large windows
+    dict(nx=8, ny=8, nz=8, nbins=3),                       # fat bins (~75 atoms): no x-sort, 3x3x3 stencil
+    dict(nx=8, ny=8, nz=8, nbins=4, halfneigh=0),          # ~32 atoms per bin
+    dict(nx=8, ny=8, nz=8, nbins=13),                      # thin bins: stencil wider than the tiling supports
+    dict(nx=6, ny=9, nz=7, nbins=9, halfneigh=1, ghost_newton=0),
+]
+
+
+@pytest.mark.parametrize("case", range(len(ODD_CASES)))
+def test_unusual_geometries_lists_and_time_loop(case):
+    kw = dict(ODD_CASES[case])
+    cfg = Config(ntimes=40, thermo_nstat=10, **kw)
+    o = Oracle(cfg, "f64")
+    c = context_from_oracle(o)
+    c.exchange()
+    c.borders()
+    half, gn = o.geti("halfneigh"), o.geti("ghost_newton")
+    mxn, total = c.build(half, gn, 100)
+    num, nb = c.neigh_download()
+    onum, onb = o.numneigh(), o.neighbors()
+    assert mxn == o.geti("maxneighs") and total == int(onum.sum())
+    assert np.array_equal(num, onum)
+    for i in range(o.nlocal):
+        assert np.array_equal(nb[i, :num[i]], onb[i, :num[i]]), f"row {i}"
+    samples, _ = c.run(run_params(o, 40))
+    got = thermo_from_samples(o, samples)
+    o.run(40)
+    st, T, U, P = o.thermo_log()
+    pscale = max(1.0, float(np.max(np.abs(P))))
+    for (step, t, e, p), tw, ew, pw in zip(got, T[1:], U[1:], P[1:]):
+        assert abs(t - tw) <= 1e-9 * abs(tw) and abs(e - ew) <= 1e-9 * abs(ew) and abs(p - pw) <= 1e-8 * pscale, (step, case)
+    assert c.query("total_neigh") == int(o.numneigh().sum())
+    print(case, "list_tile", c.query("list_tile"), "xsorted", c.query("list_xsorted"), "fallbacks", c.query("tile_fallbacks"),
+          "max halo", c.query("tile_max_halo"))
