@@ -271,6 +271,9 @@ def own_arm(a, n_gpus, rank, local_rank):
     ctx.set_option("tile_lists", a.tile)      # effective from the next neighbor build (inside the warm-up)
     if not a.p2p:
         ctx.set_option("p2p_halo", 0)
+    for kv in a.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     natoms = sim.geti("natoms")
     stream = torch.cuda.ExternalStream(ctx.stream)
 
@@ -431,6 +434,7 @@ def main():
     ap.add_argument("--tile", type=int, default=1, help="1: tile-resident neighbor lists + shared-memory force kernel (default); "
                                                         "0: classic rows of global ids (gather / scatter kernels)")
     ap.add_argument("--p2p", type=int, default=1, help="N>1: 1 = forward halo over peer-memory windows (default), 0 = NCCL send/recv")
+    ap.add_argument("--opt", action="append", default=[], help="library switch key=value (mmd_set_option), repeatable; for A/B runs")
     ap.add_argument("--no-e2e", dest="no_e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     a = ap.parse_args()

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -19,6 +20,7 @@
 #include "neighbor_kernels.cuh"
 #include "scan.cuh"
 #include "tile_kernels.cuh"
+#include "tile_dealt_kernels.cuh"
 #include "tile_eam_kernels.cuh"
 
 #ifdef MMD_WITH_NCCL
@@ -167,6 +169,12 @@ struct mmd_ctx {
   int tcap_floor = 0;       // raised when a build overflowed its rows
   int tile_max_h = 0, tile_max_full = 0;
   int tile_builds = 0, tile_fallbacks = 0;
+  // bank-dealt copy of the rows (tile_dealt_kernels.cuh): what the LJ force kernel walks
+  bool tile_dealt = true;   // option "tile_dealt"
+  bool list_dealt = false;  // trowsq holds the current list
+  DevBuf trowsq;
+  int tcapq = 0;            // dealt row capacity (16-bit entries, multiple of 32)
+  std::set<const void*> smem_optin;  // kernels of this context's device already opted in to > 48 KB dynamic shared memory
 
   // Force
   bool have_lj = false, lj_uniform = true;
@@ -259,6 +267,14 @@ static int phase_collect(mmd_ctx* c) {
 }
 
 static const int TPB = 256;
+// > 48 KB of dynamic shared memory is a per-device, per-kernel opt-in: remembered per context (one context = one device)
+template <class K> static int smem_optin(mmd_ctx* c, K kern) {
+  const void* key = reinterpret_cast<const void*>(kern);
+  if (c->smem_optin.count(key)) return MMD_OK;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+  c->smem_optin.insert(key);
+  return MMD_OK;
+}
 static int launch_fail(int line, cudaError_t e) {
   return set_err(MMD_ERR_CUDA, "mmd_device.cu:%d kernel launch: %s", line, cudaGetErrorString(e));
 }
@@ -554,6 +570,12 @@ template <class T> struct Impl {
       B.binsize[0] = 1.0 / c->geo.bininvx; B.binsize[1] = 1.0 / c->geo.bininvy; B.binsize[2] = 1.0 / c->geo.bininvz;
       B.mbinlo[0] = c->geo.mbinxlo; B.mbinlo[1] = c->geo.mbinylo; B.mbinlo[2] = c->geo.mbinzlo;
     }
+    // the interval build's footprint can exceed the force kernel's (FP32: ~13 B per window atom + tables): windows then
+    // stay in CSR order and the table build / classic rows take over
+    if (xsorted && build3_smem_bytes<T>(g, g.hcap, !B.uniform_cut) > (size_t)(227 * 1024 - 2048)) {
+      xsorted = false;
+      CU(cudaMemcpyAsync(c->tile_slots.p, c->bin_atoms.p, (size_t)nall * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    }
     const size_t b2_smem = build2_smem_bytes<T>(g, g.hcap, !B.uniform_cut);
     const bool use_b2 = c->tile_build2 && c->nsruns <= TB2_MAXSR && b2_smem <= (size_t)(227 * 1024 - 2048) &&
                         c->tile_max_h <= TB2_MAXH;
@@ -578,17 +600,9 @@ template <class T> struct Impl {
       c->d_scal + 10, c->d_total
       if (xsorted) {
         const size_t b3_smem = build3_smem_bytes<T>(g, g.hcap, !B.uniform_cut);
-        static bool attr3_done = false;
-        const int smax = 227 * 1024 - 2048;
-        if (!attr3_done) {
-          CU(cudaFuncSetAttribute(neigh_build_tile3_kernel<T, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-          CU(cudaFuncSetAttribute(neigh_build_tile3_kernel<T, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-          CU(cudaFuncSetAttribute(neigh_build_tile3_kernel<T, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-          CU(cudaFuncSetAttribute(neigh_build_tile3_kernel<T, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-          CU(cudaFuncSetAttribute(neigh_build_tile3_kernel<T, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-          CU(cudaFuncSetAttribute(neigh_build_tile3_kernel<T, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-          attr3_done = true;
-        }
+        MM(smem_optin(c, neigh_build_tile3_kernel<T, 0, 1>)); MM(smem_optin(c, neigh_build_tile3_kernel<T, 1, 1>));
+        MM(smem_optin(c, neigh_build_tile3_kernel<T, 2, 1>)); MM(smem_optin(c, neigh_build_tile3_kernel<T, 0, 0>));
+        MM(smem_optin(c, neigh_build_tile3_kernel<T, 1, 0>)); MM(smem_optin(c, neigh_build_tile3_kernel<T, 2, 0>));
 #define NB3_ARGS                                                                                                          \
   c->x.as<V>(), c->nlocal, c->bin_start.as<int>(), c->tile_slots.as<int>(), c->mbins, c->sruns.as<StencilRun>(), c->nsruns, \
       c->cutneighsq.as<T>(), c->ntypes, g, B, c->tile_runs.as<int2>(), c->tile_center.as<int4>(), c->tile_info.as<int2>(),  \
@@ -605,17 +619,9 @@ template <class T> struct Impl {
         }
 #undef NB3_ARGS
       } else if (use_b2) {
-        static bool attr_done = false;
-        const int smax = 227 * 1024 - 2048;
-        if (!attr_done) {
-          CU(cudaFuncSetAttribute(neigh_build_tile2_kernel<T, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-          CU(cudaFuncSetAttribute(neigh_build_tile2_kernel<T, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-          CU(cudaFuncSetAttribute(neigh_build_tile2_kernel<T, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-          CU(cudaFuncSetAttribute(neigh_build_tile2_kernel<T, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-          CU(cudaFuncSetAttribute(neigh_build_tile2_kernel<T, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-          CU(cudaFuncSetAttribute(neigh_build_tile2_kernel<T, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-          attr_done = true;
-        }
+        MM(smem_optin(c, neigh_build_tile2_kernel<T, 0, 1>)); MM(smem_optin(c, neigh_build_tile2_kernel<T, 1, 1>));
+        MM(smem_optin(c, neigh_build_tile2_kernel<T, 2, 1>)); MM(smem_optin(c, neigh_build_tile2_kernel<T, 0, 0>));
+        MM(smem_optin(c, neigh_build_tile2_kernel<T, 1, 0>)); MM(smem_optin(c, neigh_build_tile2_kernel<T, 2, 0>));
         if (B.uniform_cut) {
           if (mode == 0) LAUNCH_SMEM(c, (neigh_build_tile2_kernel<T, 0, 1>), g.ntiles, TB2_THREADS, b2_smem, NB2_ARGS);
           if (mode == 1) LAUNCH_SMEM(c, (neigh_build_tile2_kernel<T, 1, 1>), g.ntiles, TB2_THREADS, b2_smem, NB2_ARGS);
@@ -656,6 +662,20 @@ template <class T> struct Impl {
     c->list_tile = true;
     c->list_xsorted = xsorted;
     c->tile_builds++;
+    // bank-dealt copy of the rows for the LJ force kernel (tile_dealt_kernels.cuh)
+    c->list_dealt = false;
+    if (c->tile_dealt && !c->have_eam) {
+      const int nrows = std::max(nall, 1);
+      c->tcapq = dealt_capacity(std::min(c->tile_max_full, c->tcap));
+      const size_t dsm = deal_smem_bytes(c->tcapq);
+      if (dsm <= (size_t)(227 * 1024 - 2048)) {
+        MM(c->trowsq.reserve((size_t)nrows * c->tcapq * sizeof(unsigned short) + 256, c->stream, 0, 1.05));
+        MM(smem_optin(c, tile_rows_deal_kernel));
+        LAUNCH_SMEM(c, tile_rows_deal_kernel, div_up(nrows, DEAL_THREADS), DEAL_THREADS, dsm, c->trows.as<unsigned short>(),
+                    c->tnum.as<int2>(), nrows, c->tcap, c->nlocal, c->trowsq.as<unsigned short>(), c->tcapq, g.hcap - 1);
+        c->list_dealt = true;
+      }
+    }
     *done = true;
     return MMD_OK;
   }
@@ -772,12 +792,21 @@ template <class T> struct Impl {
     P.e_scale = half ? 0.5 : 1.0;
     P.v_scale = 0.5;
     const TileGeo& g = c->tgeo;
-    const size_t smem = tile_smem_bytes<T>(g.hcap, !UNI);
-    static bool attr_done = false;
-    if (!attr_done) {
-      CU(cudaFuncSetAttribute(force_lj_tile_kernel<T, EV, UNI, INTEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
-      attr_done = true;
+    if (c->list_dealt && qwin_smem_bytes<T>(g.hcap, !UNI) <= (size_t)(227 * 1024 - 2048)) {
+      LJDealtParams<T> Q;
+      Q.cutforcesq = P.cutforcesq; Q.sigma6 = P.sigma6; Q.epsilon = P.epsilon;
+      Q.k48 = (T)48 * P.epsilon * P.sigma6;
+      Q.cutforcesq_tab = P.cutforcesq_tab; Q.sigma6_tab = P.sigma6_tab; Q.epsilon_tab = P.epsilon_tab;
+      Q.ntypes = P.ntypes; Q.e_scale = P.e_scale; Q.v_scale = P.v_scale;
+      MM(smem_optin(c, force_lj_dealt_kernel<T, EV, UNI, INTEG>));
+      LAUNCH_SMEM(c, (force_lj_dealt_kernel<T, EV, UNI, INTEG>), g.ntiles, TILE_THREADS, qwin_smem_bytes<T>(g.hcap, !UNI),
+                  c->x.as<V>(), c->f.as<V>(), g, c->tile_runs.as<int2>(), c->tile_center.as<int4>(), c->tile_info.as<int2>(),
+                  c->tile_slots.as<int>(), c->trowsq.as<unsigned long long>(), c->tnum.as<int2>(), c->tcapq, c->nlocal, Q, VP,
+                  c->d_ev);
+      return MMD_OK;
     }
+    const size_t smem = tile_smem_bytes<T>(g.hcap, !UNI);
+    MM(smem_optin(c, force_lj_tile_kernel<T, EV, UNI, INTEG>));
     LAUNCH_SMEM(c, (force_lj_tile_kernel<T, EV, UNI, INTEG>), g.ntiles, TILE_THREADS, smem, c->x.as<V>(), c->f.as<V>(), g,
                 c->tile_runs.as<int2>(), c->tile_center.as<int4>(), c->tile_info.as<int2>(), c->tile_slots.as<int>(),
                 c->trows.as<unsigned short>(), c->tnum.as<int2>(), c->tcap, c->nlocal, P, VP, c->d_ev);
@@ -918,12 +947,8 @@ template <class T> struct Impl {
     const TileGeo& g = c->tgeo;
     const size_t sm1 = eam_tile_smem_bytes<T>(g.hcap, 1), sm2 = eam_tile_smem_bytes<T>(g.hcap, 2);
     if (sm2 > (size_t)(227 * 1024 - 2048)) return set_err(MMD_ERR_STATE, "force_eam: halo window too large for the tile kernels");
-    static bool attr_done = false;
-    if (!attr_done) {
-      CU(cudaFuncSetAttribute(eam_tile_kernel<T, 1, EV, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
-      CU(cudaFuncSetAttribute(eam_tile_kernel<T, 2, EV, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
-      attr_done = true;
-    }
+    MM(smem_optin(c, eam_tile_kernel<T, 1, EV, UNI>));
+    MM(smem_optin(c, eam_tile_kernel<T, 2, EV, UNI>));
     // ghosts receive no force in this scheme; keep their f at zero so that a following reverse halo is a no-op
     if (half && c->nghost > 0) CU(cudaMemsetAsync(c->f.as<V>() + c->nlocal, 0, (size_t)c->nghost * sizeof(V), c->stream));
 #define EAMT_ARGS                                                                                                     \
@@ -1555,7 +1580,7 @@ int mmd_ctx_destroy(mmd_ctx* c) {
                     &c->eam_rho_der, &c->eam_z2_val, &c->eam_z2_der, &c->eam_frho_val, &c->eam_frho_der, &c->eam_cut,
                     &c->rho, &c->fp, &c->border_tiles, &c->sendbuf, &c->recvbuf, &c->exch_flag, &c->exch_pos,
                     &c->exch_holes, &c->ghost_src, &c->ghost_shift, &c->sruns, &c->tile_runs, &c->tile_center, &c->tile_info, &c->tile_slots, &c->tile_oslot, &c->trows,
-                    &c->tnum};
+                    &c->tnum, &c->trowsq};
   for (DevBuf* b : bufs) b->release();
   for (int w = 0; w < MMD_MAX_SWAPS; w++) c->sw[w].list.release();
   for (int r = 0; r < (int)c->peer_win.size(); r++)
@@ -2013,6 +2038,8 @@ int mmd_query_int(mmd_ctx* c, const char* key, long long* value) {
   else if (k == "tile_lists") *value = c->tile_enable;
   else if (k == "fuse_force") *value = c->fuse_force && c->fuse_integrate;
   else if (k == "list_tile") *value = c->list_tile;
+  else if (k == "list_dealt") *value = c->list_tile && c->list_dealt;
+  else if (k == "tile_dealt_capacity") *value = c->tcapq;
   else if (k == "tile_ok") *value = c->tile_ok;
   else if (k == "tile_builds") *value = c->tile_builds;
   else if (k == "tile_fallbacks") *value = c->tile_fallbacks;
@@ -2039,6 +2066,8 @@ int mmd_set_option(mmd_ctx* c, const char* key, long long value) {
   } else if (k == "fuse_halo") {
     c->fuse_halo = value != 0;
     if (!c->fuse_halo) c->ghosts_resolved = false;
+  } else if (k == "tile_dealt") {  // 1: the LJ force kernel walks bank-dealt rows (quarter warp per atom); 0: one lane pair per row
+    c->tile_dealt = value != 0;     // takes effect at the next neighbor build
   } else if (k == "tile_xsort") {
     c->tile_xsort = value != 0;
   } else if (k == "tile_eam") {

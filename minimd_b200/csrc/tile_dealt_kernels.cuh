@@ -1,0 +1,423 @@
+// Bank-dealt neighbor rows and the pair-force kernel that walks them.
+//
+// Why (profiles/r1_tile_kernels.md): the first tile force kernel gave every lane its own row, so the 32 gathers of a warp
+// instruction hit unrelated shared-memory banks: 97 M LSU wavefronts per launch at -s 80 of which 51 M were bank-conflict
+// replays (LSU pipe 79 %, the binding resource).  The order of the entries inside a row is free (the export restores the
+// reference's order from the original CSR position), so a row can be laid out for the banks:
+//
+//   * a QUARTER WARP (8 lanes) owns one atom and reads 8 entries of its row per step.  The shared-memory image keeps
+//     (x,y) of an atom in one 16-byte record (FP32: x,y,z,type in one record), so the gather is an LDS.128, which the
+//     hardware serves one quarter warp per phase -- conflicts can only arise among the 8 entries of ONE row;
+//   * the row is sorted by bank class (tile-local index mod 8 = the 16-byte bank group of the record) and dealt round
+//     robin into G = ceil(n/8) groups: group g holds the sorted entries g, g+G, g+2G, ... -- one per lane.  A bank class with
+//     c entries puts ceil(c/G) of them into a group, i.e. one (no conflict) unless the class is over-represented.
+//
+// Storage: entry (group g, lane p) of a row is the 16-bit word (g>>2)*32 + p*4 + (g&3): lane p fetches the entries of
+// four consecutive groups with one 64-bit load, a quarter warp reads 64 contiguous bytes.  Rows are tcapq entries long
+// (a multiple of 32).  An entry is the plain tile-local index (the half-list flag of the build's rows is not needed by
+// the force); every slot that holds no neighbor -- (g,p) with g >= G or p*G + g >= n, up to the end of the row's last
+// 64-byte block -- holds the SENTINEL index hcap-1, a shared-memory slot the force kernel fills with a far-away position:
+// the pair loop carries no validity logic at all, a sentinel pair simply fails the cutoff test.
+//
+// The kernel evaluates every atom's complete neighborhood ("owner computes", as tile_kernels.cuh): the pair set is the
+// reference's (ref/force_lj.cpp:185-263 half, :366-449 full), forces/energy/virial agree up to summation order.
+#pragma once
+#include "tile_kernels.cuh"
+
+namespace mmd {
+
+constexpr int QL = 8;            // lanes per atom
+constexpr int QB = 4;            // groups per 64-bit row word
+constexpr int QBLK = QL * QB;    // entries per row block (64 bytes)
+
+__host__ __device__ inline int dealt_capacity(int longest_row) { return ((longest_row > 1 ? longest_row : 1) + QBLK - 1) / QBLK * QBLK; }
+
+// ---------------------------------------------------------------------------------------
+// rows in candidate order (neigh_build_tile*_kernel) -> bank-dealt rows.  One thread per row: count the 8 classes,
+// then place every entry at its dealt position inside a shared-memory copy of the row (odd word stride: the threads'
+// scattered 16-bit stores spread over the banks); the CTA writes the rows out with 16-byte stores.
+// ---------------------------------------------------------------------------------------
+constexpr int DEAL_THREADS = 128;
+__host__ __device__ inline size_t deal_smem_bytes(int tcapq) { return (size_t)DEAL_THREADS * (tcapq / 2 + 1) * 4 + DEAL_THREADS * 4; }
+
+__global__ void __launch_bounds__(DEAL_THREADS)
+tile_rows_deal_kernel(const unsigned short* __restrict__ rows, const int2* __restrict__ row_atom, int nrows, int tcap,
+                      int nlocal, unsigned short* __restrict__ rowsq, int tcapq, int sentinel) {
+  extern __shared__ __align__(16) unsigned char deal_smem[];
+  const int wstride = tcapq / 2 + 1;
+  unsigned* sw = reinterpret_cast<unsigned*>(deal_smem);
+  int* s_n = reinterpret_cast<int*>(sw + DEAL_THREADS * wstride);
+  const unsigned fill = (unsigned)sentinel | ((unsigned)sentinel << 16);
+  for (int k = threadIdx.x; k < DEAL_THREADS * wstride; k += DEAL_THREADS) sw[k] = fill;
+  __syncthreads();
+  const int q0 = blockIdx.x * DEAL_THREADS;
+  const int q = q0 + threadIdx.x;
+  int n = 0;
+  if (q < nrows) {
+    const int2 ta = row_atom[q];
+    if (ta.x >= 0 && ta.x < nlocal) n = min(min(max(ta.y, 0), tcap), tcapq);
+  }
+  s_n[threadIdx.x] = n;
+  if (n > 0) {
+    const unsigned short* __restrict__ src = rows + (size_t)q * tcap;
+    // class counts, 16 bits each: classes 0-3 in c0, 4-7 in c1
+    unsigned long long c0 = 0ull, c1 = 0ull;
+    for (int k = 0; k < n; k += 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(src + k);
+      const unsigned wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        if (k + e < n) {
+          const unsigned ent = (wds[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+          const unsigned long long inc = 1ull << ((ent & 3u) * 16u);
+          if (ent & 4u) c1 += inc; else c0 += inc;
+        }
+      }
+    }
+    // exclusive prefix over the classes (lane k of the product = sum of the lanes below k; totals < 65536)
+    const unsigned long long tot0 = ((c0 * 0x0001000100010001ull) >> 48) & 0xffffull;
+    unsigned long long p0 = c0 * 0x0001000100010000ull;
+    unsigned long long p1 = c1 * 0x0001000100010000ull + tot0 * 0x0001000100010001ull;
+    const int G = (n + QL - 1) / QL;
+    const float rG = 1.0f / (float)G;
+    unsigned short* dst = reinterpret_cast<unsigned short*>(sw + threadIdx.x * wstride);
+    for (int k = 0; k < n; k += 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(src + k);
+      const unsigned wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        if (k + e < n) {
+          const unsigned ent = (wds[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+          const unsigned sh = (ent & 3u) * 16u;
+          int t;
+          if (ent & 4u) { t = (int)((p1 >> sh) & 0xffffull); p1 += 1ull << sh; }
+          else { t = (int)((p0 >> sh) & 0xffffull); p0 += 1ull << sh; }
+          // t / G for t < 65536: (t + 0.5) / G stays >= 0.5 / G away from every integer, far above the FP32 error
+          const int p = __float2int_rd(((float)t + 0.5f) * rG);
+          const int g = t - p * G;
+          dst[(g >> 2) * QBLK + p * QB + (g & 3)] = (unsigned short)(ent & 0x7fffu);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // write out: ceil(n/32) blocks of 64 bytes per row, 16 bytes per thread and step
+  const int cpr = tcapq / 8;  // 16-byte chunks per row
+  for (int idx = threadIdx.x; idx < DEAL_THREADS * cpr; idx += DEAL_THREADS) {
+    const int r = idx / cpr, ch = idx - r * cpr;
+    const int nr = s_n[r];
+    if (ch * 8 < ((nr + QBLK - 1) / QBLK) * QBLK) {
+      const unsigned* s = sw + r * wstride + ch * 4;
+      uint4 o;
+      o.x = s[0]; o.y = s[1]; o.z = s[2]; o.w = s[3];
+      *reinterpret_cast<uint4*>(rowsq + (size_t)(q0 + r) * tcapq + ch * 8) = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Shared-memory image of a halo window for the dealt-row kernels.
+//   FP64: rec[hcap] = (x,y) 16-byte records, z[hcap]; types (per-type parameter tables only) in st[hcap]
+//   FP32: rec[hcap] = (x,y,z,type bits) 16-byte records
+// followed by the run tables and a per-warp stash of 32 finished forces (the Verlet / store epilogue runs one lane
+// per atom).
+// ---------------------------------------------------------------------------------------
+template <class T> struct QRec;
+template <> struct alignas(16) QRec<double> { double x, y; };
+template <> struct alignas(16) QRec<float> { float x, y, z, w; };
+
+template <class T> struct QWin {
+  QRec<T>* rec;
+  T* z;                // FP64 only
+  int* run_start;      // [TILE_MAXRUN]
+  int* run_off;        // [TILE_MAXRUN + 1]
+  T* stash;            // [warps][32][3]
+  unsigned char* st;   // FP64 + per-type tables only
+  __device__ __forceinline__ void carve(unsigned char* base, int hcap, int nwarps) {
+    rec = reinterpret_cast<QRec<T>*>(base);
+    unsigned char* q = base + (size_t)hcap * 16;
+    z = reinterpret_cast<T*>(q);
+    if (sizeof(T) == 8) q += (size_t)hcap * 8;
+    stash = reinterpret_cast<T*>(q);
+    q += (size_t)nwarps * 96 * sizeof(T);
+    run_start = reinterpret_cast<int*>(q);
+    run_off = run_start + TILE_MAXRUN;
+    st = reinterpret_cast<unsigned char*>(run_off + TILE_MAXRUN + 1);
+  }
+  __device__ __forceinline__ void put(int k, const Vec4<T>& v, bool types) {
+    if constexpr (sizeof(T) == 8) {
+      QRec<T> r; r.x = v.x; r.y = v.y;
+      rec[k] = r;
+      z[k] = v.z;
+      if (types) st[k] = (unsigned char)lane_to_type(v.w);
+    } else {
+      QRec<T> r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+      rec[k] = r;
+    }
+  }
+  __device__ __forceinline__ void get(int k, T& x, T& y, T& zz) const {
+    const QRec<T> r = rec[k];
+    x = r.x; y = r.y;
+    if constexpr (sizeof(T) == 8) zz = z[k]; else zz = r.z;
+  }
+  __device__ __forceinline__ void get(int k, T& x, T& y, T& zz, int& type) const {
+    const QRec<T> r = rec[k];
+    x = r.x; y = r.y;
+    if constexpr (sizeof(T) == 8) { zz = z[k]; type = (int)st[k]; }
+    else { zz = r.z; type = lane_to_type(r.w); }
+  }
+};
+template <class T> __host__ __device__ inline size_t qwin_smem_bytes(int hcap, bool with_types, int nwarps = TILE_THREADS / 32) {
+  return (size_t)hcap * (sizeof(T) == 8 ? 24 : 16) + (size_t)nwarps * 96 * sizeof(T) + (2 * TILE_MAXRUN + 1) * sizeof(int) +
+         ((with_types && sizeof(T) == 8) ? (size_t)hcap : 0) + 16;
+}
+
+template <class T, bool TYPES>
+__device__ __forceinline__ void qwin_stage(QWin<T>& S, const TileGeo& g, int t, int h, const int2* __restrict__ tile_runs,
+                                           const int* __restrict__ slots, const Vec4<T>* __restrict__ x) {
+  const int2* tr = tile_runs + (size_t)t * g.nrun;
+  for (int p = threadIdx.x; p < g.nrun; p += blockDim.x) {
+    const int2 r = tr[p];
+    S.run_start[p] = r.x;
+    S.run_off[p] = r.y;
+  }
+  if (threadIdx.x == 0) S.run_off[g.nrun] = h;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int p = w; p < g.nrun; p += nw) {
+    const int start = S.run_start[p], off = S.run_off[p], len = S.run_off[p + 1] - off;
+    for (int k = lane; k < len; k += 32) S.put(off + k, ldg4(x + __ldg(slots + start + k)), TYPES);
+  }
+  __syncthreads();
+}
+
+// one 64-bit row word = the entries of four consecutive groups; the L2::128B hint pulls the atom's next block too
+__device__ __forceinline__ unsigned long long ldg_rowq(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.global.nc.L2::128B.b64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
+// reciprocal for the pair loop.  FP64: MUFU.RCP64H seed + one third-order (Halley) step, y(1 + e + e^2) with e = 1 - x*y:
+// the seed is good to ~2^-22, so the result is good to ~2^-60 -- three DFMA instead of the four of two Newton steps,
+// and no IEEE-division slow path.  FP32: the hardware reciprocal.
+__device__ __forceinline__ double pair_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y, 1.0);
+  const double e2 = fma(e, e, e);
+  return fma(y, e2, y);
+}
+__device__ __forceinline__ float pair_rcp(float x) { return __frcp_rn(x); }
+
+template <class T> struct LJDealtParams {
+  T cutforcesq, sigma6, epsilon;
+  T k48;   // 48 * epsilon * sigma6
+  const T* cutforcesq_tab;
+  const T* sigma6_tab;
+  const T* epsilon_tab;
+  int ntypes;
+  double e_scale, v_scale;
+};
+
+// far-away position of the sentinel slot: its distance to any atom is finite (no inf/NaN) and beyond every cutoff
+template <class T> __device__ __forceinline__ T sentinel_coord() { return sizeof(T) == 8 ? (T)1e150 : (T)1e18f; }
+
+// one pair: neighbor at tile-local index lj
+template <class T, int EV, int UNIFORM>
+__device__ __forceinline__ void lj_pair(const QWin<T>& S, const LJDealtParams<T>& P, int lj, T xi, T yi, T zi, int ti,
+                                        T& fx, T& fy, T& fz, double& eng, double& vir) {
+  T xj, yj, zj;
+  int tj = 0;
+  if (UNIFORM) S.get(lj, xj, yj, zj); else S.get(lj, xj, yj, zj, tj);
+  const T dx = xi - xj, dy = yi - yj, dz = zi - zj;
+  const T rsq = dx * dx + dy * dy + dz * dz;
+  T cut, s6, k48, eps;
+  if (UNIFORM) {
+    cut = P.cutforcesq; s6 = P.sigma6; k48 = P.k48; eps = P.epsilon;
+  } else {
+    const int tij = ti * P.ntypes + tj;
+    cut = __ldg(P.cutforcesq_tab + tij); s6 = __ldg(P.sigma6_tab + tij); eps = __ldg(P.epsilon_tab + tij);
+    k48 = (T)48 * eps * s6;
+  }
+  // evaluated unconditionally (r^2 > 0 for distinct atoms; the sentinel gives a finite 3e300), accumulated under the
+  // cutoff predicate: no select, no branch
+  const bool hit = rsq < cut;
+  const T a1 = pair_rcp(rsq);
+  const T a2 = a1 * a1;
+  const T a3 = a2 * a1;
+  // F/r = 48 eps sr6 (sr6 - 0.5) / r^2 with sr6 = sigma6 / r^6 (ref/force_lj.cpp:232-235)
+  const T force = (a2 * a2) * (a3 * s6 - (T)0.5) * k48;
+  if (hit) {
+    fx += dx * force;
+    fy += dy * force;
+    fz += dz * force;
+  }
+  if (EV) {
+    const T sr6 = a3 * s6;
+    if (hit) {
+      eng += (double)((T)4 * sr6 * (sr6 - (T)1) * eps);
+      vir += (double)(rsq * force);
+    }
+  }
+}
+
+// INTEG = 1: the velocity-Verlet halves that follow the force ride in the epilogue (see VerletParams, tile_kernels.cuh)
+template <class T, int EV, int UNIFORM, int INTEG>
+__global__ void __launch_bounds__(TILE_THREADS, 2)
+force_lj_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, TileGeo g, const int2* __restrict__ tile_runs,
+                      const int4* __restrict__ tile_center, const int2* __restrict__ tile_info, const int* __restrict__ slots,
+                      const unsigned long long* __restrict__ rowsq, const int2* __restrict__ row_atom, int tcapq, int nlocal,
+                      LJDealtParams<T> P, VerletParams<T> VP, double* __restrict__ ev_out) {
+  extern __shared__ __align__(16) unsigned char tile_smem_raw[];
+  const int t = blockIdx.x;
+  const int2 inf = tile_info[t];
+  if (inf.y == 0) return;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int p = lane & (QL - 1), qg = lane >> 3;
+  const int wpr = tcapq / QB;  // 64-bit words per row
+  const unsigned long long sent4 = 0x0001000100010001ull * (unsigned long long)(g.hcap - 1);
+
+  // {atom id, row length} and the first row word of a pass are fetched one pass ahead; the very first fetch is issued
+  // before the halo window is staged
+  int cr = w;
+  int4 ce = make_int4(0, 0, 0, 0);
+  if (cr < TILE_NCENTER) ce = tile_center[(size_t)t * TILE_NCENTER + cr];
+  int2 ta_n = make_int2(-1, 0);
+  unsigned long long w_n = sent4;
+  if (ce.x + qg < ce.y) {
+    const size_t q = (size_t)(ce.z + qg);
+    ta_n = __ldg(row_atom + q);
+    w_n = ldg_rowq(rowsq + q * wpr + p);
+  }
+
+  QWin<T> S;
+  S.carve(tile_smem_raw, g.hcap, nw);
+  if (threadIdx.x == 0) {
+    Vec4<T> far;
+    far.x = far.y = far.z = sentinel_coord<T>();
+    far.w = type_to_lane<T>(0);
+    S.put(g.hcap - 1, far, !UNIFORM);
+  }
+  qwin_stage<T, !UNIFORM>(S, g, t, inf.x, tile_runs, slots, x);
+  T* stash = S.stash + w * 96;
+
+  double eng = 0.0, vir = 0.0, ke = 0.0;
+  for (; cr < TILE_NCENTER; cr += nw) {
+    if (cr != w) {  // only when the block has fewer warps than centre pencils
+      ce = tile_center[(size_t)t * TILE_NCENTER + cr];
+      ta_n = make_int2(-1, 0);
+      w_n = sent4;
+      if (ce.x + qg < ce.y) {
+        const size_t q = (size_t)(ce.z + qg);
+        ta_n = __ldg(row_atom + q);
+        w_n = ldg_rowq(rowsq + q * wpr + p);
+      }
+    }
+    for (int a0 = ce.x; a0 < ce.y; a0 += 32) {
+      const int npass = (min(32, ce.y - a0) + 3) >> 2;
+      for (int ps = 0; ps < npass; ps++) {
+        const int a = a0 + ps * 4 + qg;
+        const bool have = a < ce.y;
+        const int2 ta = ta_n;
+        // an atom owns its row whatever the row's length (an isolated atom has an empty one and still integrates)
+        const bool own = have && ta.x >= 0 && ta.x < nlocal;
+        const int n = own ? max(ta.y, 0) : 0;
+        const int aa = have ? a : ce.x;
+        const int G = (n + QL - 1) / QL;          // groups of this atom's row
+        const int nwords = (G + QB - 1) / QB;     // row words that hold them; beyond: all-sentinel words
+        const unsigned long long* __restrict__ rowq = rowsq + (size_t)(ce.z + (aa - ce.x)) * wpr + p;
+        unsigned long long w0 = nwords > 0 ? w_n : sent4;
+        unsigned long long w1 = sent4;
+        if (nwords > 1) w1 = ldg_rowq(rowq + QL);
+        {  // next pass
+          const int an = a + 4;
+          ta_n = make_int2(-1, 0);
+          w_n = sent4;
+          if (an < ce.y) {
+            const size_t q = (size_t)(ce.z + (an - ce.x));
+            ta_n = __ldg(row_atom + q);
+            w_n = ldg_rowq(rowsq + q * wpr + p);
+          }
+        }
+        const int gmax = __reduce_max_sync(0xffffffffu, G);   // the quarter warps of a pass run in lock step
+        T xi, yi, zi;
+        int ti = 0;
+        if (UNIFORM) S.get(aa, xi, yi, zi); else S.get(aa, xi, yi, zi, ti);
+        T fx = 0, fy = 0, fz = 0;
+        const int nfull = gmax >> 2;
+        for (int b = 0; b < nfull; b++) {
+          const unsigned long long cur = w0;
+          w0 = w1;
+          w1 = sent4;
+          if (b + 2 < nwords) w1 = ldg_rowq(rowq + (size_t)(b + 2) * QL);
+          // four independent pair evaluations in flight: the FP64 dependency chains overlap
+#pragma unroll
+          for (int e = 0; e < QB; e++)
+            lj_pair<T, EV, UNIFORM>(S, P, (int)((cur >> (16 * e)) & 0xffffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
+        }
+        if (gmax & 2) {
+          lj_pair<T, EV, UNIFORM>(S, P, (int)(w0 & 0xffffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
+          lj_pair<T, EV, UNIFORM>(S, P, (int)((w0 >> 16) & 0xffffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
+        }
+        if (gmax & 1)
+          lj_pair<T, EV, UNIFORM>(S, P, (int)((w0 >> ((gmax & 2) * 16)) & 0xffffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
+        fx = group_sum<QL>(fx);
+        fy = group_sum<QL>(fy);
+        fz = group_sum<QL>(fz);
+        if (p == 0) {
+          T* s = stash + (ps * 4 + qg) * 3;
+          s[0] = fx; s[1] = fy; s[2] = fz;
+        }
+      }
+      __syncwarp();
+      // ---- epilogue: one lane per atom of this block of 32 ----
+      {
+        const int a = a0 + lane;
+        int id = -1;
+        if (a < ce.y) {
+          const int2 ta = __ldg(row_atom + (size_t)(ce.z + (a - ce.x)));
+          if (ta.x >= 0 && ta.x < nlocal) id = ta.x;
+        }
+        if (id >= 0) {
+          const T fxa = stash[lane * 3 + 0], fya = stash[lane * 3 + 1], fza = stash[lane * 3 + 2];
+          if (INTEG) {
+            T xa, ya, za;
+            S.get(a, xa, ya, za);
+            Vec4<T> vi = VP.v[id];
+            vi.x += VP.dtforce * fxa;
+            vi.y += VP.dtforce * fya;
+            vi.z += VP.dtforce * fza;
+            if (EV) ke += (double)((vi.x * vi.x + vi.y * vi.y + vi.z * vi.z) * VP.mass);
+            vi.x += VP.dtforce * fxa;
+            vi.y += VP.dtforce * fya;
+            vi.z += VP.dtforce * fza;
+            Vec4<T> xo;
+            xo.x = xa + VP.dt * vi.x;
+            xo.y = ya + VP.dt * vi.y;
+            xo.z = za + VP.dt * vi.z;
+            xo.w = x[id].w;  // the type lane travels with the atom
+            VP.v[id] = vi;
+            VP.x_out[id] = xo;
+          } else {
+            Vec4<T> out;
+            out.x = fxa; out.y = fya; out.z = fza; out.w = (T)0;
+            f[id] = out;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (EV) {
+    if (INTEG) {
+      const double v3[3] = {eng * P.e_scale, vir * P.v_scale, ke};
+      block_accumulate<3>(v3, ev_out);
+    } else {
+      const double v2[2] = {eng * P.e_scale, vir * P.v_scale};
+      block_accumulate<2>(v2, ev_out);
+    }
+  }
+}
+
+}  // namespace mmd

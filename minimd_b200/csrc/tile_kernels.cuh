@@ -1141,8 +1141,9 @@ force_lj_tile_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Til
       const int a = a0 + lane / LJT_TPA;
       const int2 ta = ta_n;
       uint4 nxt = c_n;
-      const int id = (a < ce.y && ta.y > 0) ? ta.x : -1;
-      const int cnt = id >= 0 ? ta.y : 0;
+      // an atom owns its row whatever the row's length (an isolated atom has an empty one and is still stored / integrated)
+      const int id = (a < ce.y && ta.x >= 0 && ta.x < nlocal) ? ta.x : -1;
+      const int cnt = id >= 0 ? max(ta.y, 0) : 0;
       const int aa = id >= 0 ? a : ce.x;
       const unsigned short* __restrict__ row = rows + (size_t)(ce.z + (aa - ce.x)) * tcap;
       {  // next pass

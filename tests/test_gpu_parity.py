@@ -165,19 +165,23 @@ def setup_lists(o, tile=1):
     return c
 
 
+@pytest.mark.parametrize("dealt", [1, 0])
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 @pytest.mark.parametrize("half,gn", [(1, 1), (1, 0), (0, 0)])
 @pytest.mark.parametrize("size", [(8, 8, 8), (5, 7, 9)])
-def test_lj_tile_force_energy_virial(half, gn, size, prec):
+def test_lj_tile_force_energy_virial(half, gn, size, prec, dealt):
     """Tile-resident lists: every local atom's force is complete after the kernel (no scatter, no reverse
-    halo), so half+ghost_newton is compared with the oracle AFTER its reverse_communicate."""
+    halo), so half+ghost_newton is compared with the oracle AFTER its reverse_communicate.
+    dealt=1: bank-dealt rows walked by a quarter warp per atom (the default); dealt=0: one lane pair per row."""
     o = melted(dict(nx=size[0], ny=size[1], nz=size[2], halfneigh=half, ghost_newton=gn), 40, prec)
     c = context_from_oracle(o)
     c.set_option("tile_xsort", 1 if size[0] == 8 else 0)   # one size per build flavour
+    c.set_option("tile_dealt", dealt)
     c.exchange()
     c.borders()
     c.build(half, gn, 100)
     assert c.query("list_tile") == 1
+    assert c.query("list_dealt") == dealt
     o.seti("evflag", 1)
     o.call("force_compute")
     if half and gn:
@@ -362,6 +366,34 @@ def test_time_loop_matches_oracle(force, half, gn, prec, tol, tile):
         assert c.query("maxneighs") == o.geti("maxneighs")
 
 
+@pytest.mark.parametrize("opts", [dict(tile_lists=1, tile_dealt=1), dict(tile_lists=1, tile_dealt=0),
+                                  dict(tile_lists=1, tile_dealt=1, fuse_force=0), dict(tile_lists=0)])
+def test_isolated_atoms_are_still_integrated(opts):
+    """A gas so thin that no atom has a neighbor inside cutneigh (every row is empty): the atoms must still be owned by
+    their rows -- forces stored as zero, velocities and positions advanced -- in every list format and fusion mode."""
+    cfg = Config(nx=6, ny=6, nz=6, ntimes=40, rho=0.02, halfneigh=1, ghost_newton=1, thermo_nstat=10)
+    o = Oracle(cfg, "f64")
+    c = context_from_oracle(o)
+    for k, v in opts.items():
+        c.set_option(k, v)
+    c.exchange()
+    c.borders()
+    c.build(1, 1, 100)
+    assert c.query("total_neigh") == 0
+    samples, _ = c.run(run_params(o, 40))
+    o.run(40)
+    nl = o.nlocal
+    assert c.counts()[0] == nl
+    d = c.download("xvf", count=nl)
+    assert_close(d["x"], o.x(nl), 1e-13, "x")
+    assert_close(d["v"], o.v(nl), 1e-13, "v")
+    assert maxabs(d["f"]) == 0.0
+    st, T, U, P = o.thermo_log()
+    got = thermo_from_samples(o, samples)
+    for (step, t, e, p), tw in zip(got, T[1:]):
+        assert abs(t - tw) <= 1e-12 * abs(tw) and e == 0.0
+
+
 # ------------------------------------------------------------------------------------------
 # run-time switches: every optional fusion must reproduce the unfused path
 # ------------------------------------------------------------------------------------------
@@ -387,9 +419,10 @@ def test_fused_paths_reproduce_the_unfused_ones(prec):
     assert np.array_equal(halo[1], base[1]) and np.array_equal(halo[2], base[2])
     assert halo[3] < base[3]
     # Verlet halves in one kernel / in the force kernel's epilogue: same operations in the same order
-    for opts in (dict(fuse_halo=1, fuse_force=0, fuse_integrate=1), dict(fuse_halo=1, fuse_force=1, fuse_integrate=1)):
+    for opts in (dict(fuse_halo=1, fuse_force=0, fuse_integrate=1), dict(fuse_halo=1, fuse_force=1, fuse_integrate=1),
+                 dict(fuse_halo=1, fuse_force=1, fuse_integrate=1, tile_dealt=0)):
         got = _run_with(opts, prec)
-        tol = 1e-12 if prec == "f64" else 1e-5
+        tol = 1e-12 if prec == "f64" else 5e-5
         assert_close(got[1], base[1], tol, f"x {opts}")
         assert_close(got[2], base[2], tol, f"v {opts}")
         for (s0, m0, e0, v0), (s1, m1, e1, v1) in zip(base[0], got[0]):
