@@ -6,6 +6,7 @@
 #pragma once
 #include "common.cuh"
 #include "scan.cuh"
+#include "xs_mirror.cuh"
 
 namespace mmd {
 
@@ -128,7 +129,7 @@ struct SwapPairDev {
 // (half-list prologue, ref/force_lj.cpp:195-199).
 template <class T, int ZERO_F>
 __global__ void halo_forward_self_kernel(Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, SwapPairDev sp, T xprd,
-                                         T yprd, T zprd) {
+                                         T yprd, T zprd, XsMirror<T> M) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   int s = 0;
   if (k >= sp.count[0]) { k -= sp.count[0]; s = 1; }
@@ -140,6 +141,7 @@ __global__ void halo_forward_self_kernel(Vec4<T>* __restrict__ x, Vec4<T>* __res
     p.z = p.z + sp.flag[s][2] * zprd;
   }
   x[sp.first[s] + k] = p;
+  M.put_atom(sp.first[s] + k, p);
   if (ZERO_F) {
     Vec4<T> z; z.x = z.y = z.z = z.w = (T)0;
     f[sp.first[s] + k] = z;
@@ -170,7 +172,7 @@ __global__ void ghost_resolve_kernel(const int* __restrict__ list, int count, in
 }
 template <class T>
 __global__ void halo_forward_resolved_kernel(Vec4<T>* __restrict__ x, int nlocal, int nghost, const int* __restrict__ src,
-                                             const int* __restrict__ shift, T xprd, T yprd, T zprd) {
+                                             const int* __restrict__ shift, T xprd, T yprd, T zprd, XsMirror<T> M) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= nghost) return;
   Vec4<T> p = x[src[g]];
@@ -180,6 +182,7 @@ __global__ void halo_forward_resolved_kernel(Vec4<T>* __restrict__ x, int nlocal
   if (sy) p.y = p.y + sy * yprd;
   if (sz) p.z = p.z + sz * zprd;
   x[nlocal + g] = p;
+  M.put_atom(nlocal + g, p);
 }
 
 // self-swap reverse: f[list[k]] += f[first+k]  (pack_reverse + unpack_reverse fused).
@@ -320,7 +323,7 @@ template <class T, int ZERO_F>
 __global__ void halo_p2p_unpack_kernel(Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, int first0, int n0, int first1,
                                        int n1, const T* __restrict__ src0, const T* __restrict__ src1,
                                        const unsigned long long* flag0, const unsigned long long* flag1,
-                                       unsigned long long epoch, int* __restrict__ status) {
+                                       unsigned long long epoch, int* __restrict__ status, XsMirror<T> M) {
   if (threadIdx.x == 0) {
     const long long t0 = clock64();
     while (ld_acquire_sys(flag0) < epoch || ld_acquire_sys(flag1) < epoch) {
@@ -341,6 +344,7 @@ __global__ void halo_p2p_unpack_kernel(Vec4<T>* __restrict__ x, Vec4<T>* __restr
   p.y = __ldcg(b + 1);
   p.z = __ldcg(b + 2);
   x[dst] = p;
+  M.put_atom(dst, p);
   if (ZERO_F) {
     Vec4<T> z; z.x = z.y = z.z = z.w = (T)0;
     f[dst] = z;
@@ -349,7 +353,7 @@ __global__ void halo_p2p_unpack_kernel(Vec4<T>* __restrict__ x, Vec4<T>* __restr
 
 template <class T, int ZERO_F>
 __global__ void halo_unpack_x_pair_kernel(Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, int first0, int n0, int first1,
-                                          int n1, const T* __restrict__ buf) {
+                                          int n1, const T* __restrict__ buf, XsMirror<T> M) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n0 + n1) return;
   const int dst = g < n0 ? first0 + g : first1 + (g - n0);
@@ -358,6 +362,7 @@ __global__ void halo_unpack_x_pair_kernel(Vec4<T>* __restrict__ x, Vec4<T>* __re
   p.y = buf[(size_t)3 * g + 1];
   p.z = buf[(size_t)3 * g + 2];
   x[dst] = p;
+  M.put_atom(dst, p);
   if (ZERO_F) {
     Vec4<T> z; z.x = z.y = z.z = z.w = (T)0;
     f[dst] = z;

@@ -174,6 +174,11 @@ struct mmd_ctx {
   bool list_dealt = false;  // trowsq holds the current list
   DevBuf trowsq;
   int tcapq = 0;            // dealt row capacity (16-bit entries, multiple of 32)
+  int tile_max_rows = 0;    // most rows (atoms of the own bins) of any tile: sizes the force kernel's stash
+  // slot-ordered mirror of the positions (xs_mirror.cuh), double-buffered like x / x_alt
+  DevBuf xs_rec[2], xs_z[2], slot_of, xs_types;
+  int xs_cur = 0;
+  bool xs_valid = false;    // the current mirror buffer agrees with x[] for every binned atom
   std::set<const void*> smem_optin;  // kernels of this context's device already opted in to > 48 KB dynamic shared memory
 
   // Force
@@ -214,7 +219,8 @@ struct mmd_ctx {
 
   // device scalars + pinned mirror
   // d_scal ints : [0] status, [1] max_n, [2] max_bin, [3] border total 0, [4] border total 1, [5] scan total,
-  //               [6..9] exchange/border counts, [10] max full row, [11] max halo window, [12] tile status
+  //               [6..9] exchange/border counts, [10] max full row, [11] max halo window, [12] tile status,
+  //               [13] tile row counter, [14] max rows of a tile
   // d_ev doubles: [0] eng, [1] virial, [2] sum m v^2, [3] embed energy
   int* d_scal = nullptr;
   unsigned long long* d_total = nullptr;
@@ -382,6 +388,7 @@ template <class T> struct Impl {
     CU(cudaMemsetAsync(c->f.p, 0, (size_t)c->cap * sizeof(V), c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->nlocal = nlocal;
+    c->xs_valid = false;
     c->neigh_rows = -1;  // lists and ghost tables refer to the previous atoms
     c->ghosts_resolved = false;
     for (int w = 0; w < MMD_MAX_SWAPS; w++) c->sw[w].sendnum = c->sw[w].recvnum = c->sw[w].firstrecv = 0;
@@ -393,6 +400,7 @@ template <class T> struct Impl {
     const size_t nb = (size_t)count * pad * sizeof(T);
     const int g = div_up(count, TPB);
     if (x) {
+      c->xs_valid = false;  // positions change behind the mirror's back: refilled before the next dealt force launch
       MM(c->stage_a.reserve(nb, c->stream));
       CU(cudaMemcpyAsync(c->stage_a.p, x, nb, cudaMemcpyHostToDevice, c->stream));
       LAUNCH(c, pack_x_kernel<T>, g, TPB, c->stage_a.as<T>(), nullptr, count, pad, c->x.as<V>() + first, 1);
@@ -439,6 +447,7 @@ template <class T> struct Impl {
 
   static int pbc(mmd_ctx* c) {
     if (!c->have_box) return set_err(MMD_ERR_STATE, "pbc: mmd_atom_set_box not called");
+    c->xs_valid = false;
     LAUNCH(c, pbc_kernel<T>, div_up(c->nlocal, TPB), TPB, c->x.as<V>(), c->nlocal, (T)c->prd[0], (T)c->prd[1],
            (T)c->prd[2]);
     return MMD_OK;
@@ -480,7 +489,7 @@ template <class T> struct Impl {
 
   static int read_status(mmd_ctx* c) {  // status + running max bin occupancy
     CU(cudaMemcpyAsync(c->h_scal, c->d_scal, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(c->h_scal + 10, c->d_scal + 10, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_scal + 10, c->d_scal + 10, 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->max_bin_seen = std::max(c->max_bin_seen, c->h_scal[2]);
     if (c->h_scal[0] & 1) return set_err(MMD_ERR_STATE, "atom outside the bin grid (lost atom / bad coordinates)");
@@ -494,6 +503,7 @@ template <class T> struct Impl {
            c->v.as<V>(), c->x_alt.as<V>(), c->v_alt.as<V>());
     std::swap(c->x, c->x_alt);  // pointer swap, ref/atom.cpp:409-418
     std::swap(c->v, c->v_alt);
+    c->xs_valid = false;
     return MMD_OK;
   }
 
@@ -501,6 +511,43 @@ template <class T> struct Impl {
   // EAM: the owner-computes passes (tile_eam_kernels.cuh) evaluate every pair twice and the pair math is table-bound --
   // measured slower than the classic half-list path at -s 64 (1.38 vs 0.99 ms per step), so they are opt-in ("tile_eam")
   static bool want_tile(mmd_ctx* c) { return c->tile_enable && c->tile_ok && (!c->have_eam || c->tile_eam); }
+
+  // ---- slot-ordered mirror of the positions (xs_mirror.cuh) -----------------------------------
+  static XsMirror<T> mirror(mmd_ctx* c, int which) {
+    XsMirror<T> M;
+    M.rec = c->xs_rec[which].as<QRec<T>>();
+    M.z = c->xs_z[which].as<T>();
+    M.slot_of = c->slot_of.as<int>();
+    return M;
+  }
+  // the mirror the atom-moving kernels have to keep current (none unless a dealt list with a valid mirror exists)
+  static XsMirror<T> live_mirror(mmd_ctx* c) {
+    if (c->list_tile && c->list_dealt && c->xs_valid && c->neigh_rows == c->nlocal) return mirror(c, c->xs_cur);
+    XsMirror<T> M;
+    M.rec = nullptr; M.z = nullptr; M.slot_of = nullptr;
+    return M;
+  }
+  // (re)build the current mirror buffer from x[] for every binned atom
+  static int xs_fill(mmd_ctx* c) {
+    const int nall = c->nlocal + c->nghost;
+    const size_t cap = (size_t)std::max(c->cap, nall) + 64;
+    for (int b = 0; b < 2; b++) {
+      MM(c->xs_rec[b].reserve(cap * 16, c->stream));
+      if (sizeof(T) == 8) MM(c->xs_z[b].reserve(cap * 8, c->stream));
+    }
+    MM(c->slot_of.reserve(cap * sizeof(int), c->stream));
+    MM(c->xs_types.reserve(cap, c->stream));
+    LAUNCH(c, xs_fill_kernel<T>, div_up(nall, TPB), TPB, c->x.as<V>(), c->tile_slots.as<int>(), nall, mirror(c, c->xs_cur),
+           c->slot_of.as<int>(), c->xs_types.as<unsigned char>());
+    c->xs_valid = true;
+    return MMD_OK;
+  }
+  // local atoms were moved by an unfused integrator: copy them into the mirror
+  static int xs_refresh_locals(mmd_ctx* c) {
+    const XsMirror<T> M = live_mirror(c);
+    if (M.rec) LAUNCH(c, xs_refresh_kernel<T>, div_up(c->nlocal, TPB), TPB, c->x.as<V>(), 0, c->nlocal, M);
+    return MMD_OK;
+  }
 
   // tile-resident build (tile_kernels.cuh).  *done = false when the tiling does not fit this state (halo window
   // larger than the shared-memory capacity, stencil leaving the grid): the caller builds classic rows instead.
@@ -529,10 +576,10 @@ template <class T> struct Impl {
     // one row per binned atom, numbered tile by tile (the rows of ghost atoms are never touched)
     MM(c->tnum.reserve((size_t)std::max(nall, 1) * sizeof(int2), c->stream, 0, 1.1));
     CU(cudaMemsetAsync(c->tnum.p, 0xff, (size_t)std::max(nall, 1) * sizeof(int2), c->stream));
-    CU(cudaMemsetAsync(c->d_scal + 10, 0, 4 * sizeof(int), c->stream));
+    CU(cudaMemsetAsync(c->d_scal + 10, 0, 5 * sizeof(int), c->stream));
     LAUNCH(c, tile_table_kernel, div_up(g.ntiles, 4), 128, g, c->bin_start.as<int>(), c->bin_atoms.as<int>(), c->mbins,
            c->nlocal, c->tile_runs.as<int2>(), c->tile_center.as<int4>(), c->tile_info.as<int2>(), c->d_scal + 11,
-           c->d_scal + 13);
+           c->d_scal + 13, c->d_scal + 14);
     // the windows' slot -> atom map: a private copy of the CSR bins, every bin sorted by x when the interval build is used
     bool xsorted = c->tile_xsort && c->tile_build2 && c->nsruns <= 32;
     if (xsorted) {
@@ -551,6 +598,7 @@ template <class T> struct Impl {
       CU(cudaMemcpyAsync(c->tile_slots.p, c->bin_atoms.p, (size_t)nall * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
     }
     c->tile_max_h = c->h_scal[11];
+    c->tile_max_rows = c->h_scal[14];
     const int hcap_limit = (int)((227 * 1024 - 4096) / (3 * sizeof(T) + 1)) & ~63;
     if (c->tile_max_h > hcap_limit) {
       c->tile_fallbacks++;
@@ -674,6 +722,8 @@ template <class T> struct Impl {
         LAUNCH_SMEM(c, tile_rows_deal_kernel, div_up(nrows, DEAL_THREADS), DEAL_THREADS, dsm, c->trows.as<unsigned short>(),
                     c->tnum.as<int2>(), nrows, c->tcap, c->nlocal, c->trowsq.as<unsigned short>(), c->tcapq, g.hcap - 1);
         c->list_dealt = true;
+        c->xs_valid = false;
+        MM(xs_fill(c));
       }
     }
     *done = true;
@@ -792,17 +842,21 @@ template <class T> struct Impl {
     P.e_scale = half ? 0.5 : 1.0;
     P.v_scale = 0.5;
     const TileGeo& g = c->tgeo;
-    if (c->list_dealt && qwin_smem_bytes<T>(g.hcap, !UNI) <= (size_t)(227 * 1024 - 2048)) {
+    const int scap = (c->tile_max_rows + 7) & ~7;
+    if (c->list_dealt && qwin_smem_bytes<T>(g.hcap, !UNI, scap) <= (size_t)(227 * 1024 - 2048)) {
+      if (!c->xs_valid) MM(xs_fill(c));
       LJDealtParams<T> Q;
       Q.cutforcesq = P.cutforcesq; Q.sigma6 = P.sigma6; Q.epsilon = P.epsilon;
       Q.k48 = (T)48 * P.epsilon * P.sigma6;
       Q.cutforcesq_tab = P.cutforcesq_tab; Q.sigma6_tab = P.sigma6_tab; Q.epsilon_tab = P.epsilon_tab;
       Q.ntypes = P.ntypes; Q.e_scale = P.e_scale; Q.v_scale = P.v_scale;
       MM(smem_optin(c, force_lj_dealt_kernel<T, EV, UNI, INTEG>));
-      LAUNCH_SMEM(c, (force_lj_dealt_kernel<T, EV, UNI, INTEG>), g.ntiles, TILE_THREADS, qwin_smem_bytes<T>(g.hcap, !UNI),
+      LAUNCH_SMEM(c, (force_lj_dealt_kernel<T, EV, UNI, INTEG>), g.ntiles, TILE_THREADS, qwin_smem_bytes<T>(g.hcap, !UNI, scap),
                   c->x.as<V>(), c->f.as<V>(), g, c->tile_runs.as<int2>(), c->tile_center.as<int4>(), c->tile_info.as<int2>(),
-                  c->tile_slots.as<int>(), c->trowsq.as<unsigned long long>(), c->tnum.as<int2>(), c->tcapq, c->nlocal, Q, VP,
-                  c->d_ev);
+                  mirror(c, c->xs_cur), c->xs_types.as<unsigned char>(), c->trowsq.as<unsigned long long>(), c->tnum.as<int2>(),
+                  c->tcapq, c->nlocal, scap, Q, VP, mirror(c, c->xs_cur ^ 1), c->d_ev);
+      if (INTEG) c->xs_cur ^= 1;  // the epilogue wrote the local atoms' new positions into the other buffer (ghosts follow
+                                  // with the next forward halo, as in x_alt)
       return MMD_OK;
     }
     const size_t smem = tile_smem_bytes<T>(g.hcap, !UNI);
@@ -994,7 +1048,7 @@ template <class T> struct Impl {
     const int g = div_up(c->nlocal, TPB);
     if (zero_f) LAUNCH(c, (initial_integrate_kernel<T, 1>), g, TPB, c->x.as<V>(), c->v.as<V>(), c->f.as<V>(), c->nlocal, (T)dt, (T)dtforce);
     else LAUNCH(c, (initial_integrate_kernel<T, 0>), g, TPB, c->x.as<V>(), c->v.as<V>(), c->f.as<V>(), c->nlocal, (T)dt, (T)dtforce);
-    return MMD_OK;
+    return xs_refresh_locals(c);
   }
   static int final_(mmd_ctx* c, double dtforce, bool ke, double mass) {
     const int g = div_up(c->nlocal, TPB);
@@ -1014,7 +1068,7 @@ template <class T> struct Impl {
     } else {
       LAUNCH(c, (final_initial_integrate_kernel<T, 0>), g, TPB, c->x.as<V>(), c->v.as<V>(), c->f.as<V>(), c->nlocal, (T)dt, (T)dtforce, (T)mass, c->d_ev + 2);
     }
-    return MMD_OK;
+    return xs_refresh_locals(c);
   }
   static int sum_mv2(mmd_ctx* c, double mass, double* out) {
     CU(cudaMemsetAsync(c->d_ev + 2, 0, sizeof(double), c->stream));
@@ -1078,7 +1132,7 @@ template <class T> struct Impl {
     const T px = (T)c->prd[0], py = (T)c->prd[1], pz = (T)c->prd[2];
     if (c->ghosts_resolved && !zero_ghost_f) {
       LAUNCH(c, halo_forward_resolved_kernel<T>, div_up(c->nghost, TPB), TPB, c->x.as<V>(), c->nlocal, c->nghost,
-             c->ghost_src.as<int>(), c->ghost_shift.as<int>(), px, py, pz);
+             c->ghost_src.as<int>(), c->ghost_shift.as<int>(), px, py, pz, live_mirror(c));
       return MMD_OK;
     }
     for (int w = 0; w < c->swaps.nswap; w += 2) {
@@ -1086,8 +1140,8 @@ template <class T> struct Impl {
       if (is_self(c, w) && (nsw < 2 || is_self(c, w + 1))) {
         const SwapPairDev sp = pair_desc(c, w, nsw);
         const int n = sp.count[0] + sp.count[1];
-        if (zero_ghost_f) LAUNCH(c, (halo_forward_self_kernel<T, 1>), div_up(n, TPB), TPB, c->x.as<V>(), c->f.as<V>(), sp, px, py, pz);
-        else LAUNCH(c, (halo_forward_self_kernel<T, 0>), div_up(n, TPB), TPB, c->x.as<V>(), c->f.as<V>(), sp, px, py, pz);
+        if (zero_ghost_f) LAUNCH(c, (halo_forward_self_kernel<T, 1>), div_up(n, TPB), TPB, c->x.as<V>(), c->f.as<V>(), sp, px, py, pz, live_mirror(c));
+        else LAUNCH(c, (halo_forward_self_kernel<T, 0>), div_up(n, TPB), TPB, c->x.as<V>(), c->f.as<V>(), sp, px, py, pz, live_mirror(c));
       } else {
 #ifdef MMD_WITH_NCCL
         if (nsw != 2) return set_err(MMD_ERR_STATE, "communicate: odd swap count");
@@ -1107,8 +1161,8 @@ template <class T> struct Impl {
           const T* s0 = reinterpret_cast<const T*>(p2p_region(c->win, par, w));
           const T* s1 = reinterpret_cast<const T*>(p2p_region(c->win, par, w + 1));
           const int ug = std::max(1, div_up(nr0 + nr1, TPB));
-          if (zero_ghost_f) LAUNCH(c, (halo_p2p_unpack_kernel<T, 1>), ug, TPB, c->x.as<V>(), c->f.as<V>(), c->sw[w].firstrecv, nr0, c->sw[w + 1].firstrecv, nr1, s0, s1, p2p_flag(c->win, w), p2p_flag(c->win, w + 1), epoch, c->d_scal + 0);
-          else LAUNCH(c, (halo_p2p_unpack_kernel<T, 0>), ug, TPB, c->x.as<V>(), c->f.as<V>(), c->sw[w].firstrecv, nr0, c->sw[w + 1].firstrecv, nr1, s0, s1, p2p_flag(c->win, w), p2p_flag(c->win, w + 1), epoch, c->d_scal + 0);
+          if (zero_ghost_f) LAUNCH(c, (halo_p2p_unpack_kernel<T, 1>), ug, TPB, c->x.as<V>(), c->f.as<V>(), c->sw[w].firstrecv, nr0, c->sw[w + 1].firstrecv, nr1, s0, s1, p2p_flag(c->win, w), p2p_flag(c->win, w + 1), epoch, c->d_scal + 0, live_mirror(c));
+          else LAUNCH(c, (halo_p2p_unpack_kernel<T, 0>), ug, TPB, c->x.as<V>(), c->f.as<V>(), c->sw[w].firstrecv, nr0, c->sw[w + 1].firstrecv, nr1, s0, s1, p2p_flag(c->win, w), p2p_flag(c->win, w + 1), epoch, c->d_scal + 0, live_mirror(c));
           c->p2p_calls++;
           continue;
         }
@@ -1117,8 +1171,8 @@ template <class T> struct Impl {
         LAUNCH(c, halo_pack_x_pair_kernel<T>, div_up(ns0 + ns1, TPB), TPB, c->x.as<V>(), sp, px, py, pz, c->sendbuf.as<T>());
         MM(sendrecv_pair(c, c->sendbuf.as<T>(), (size_t)3 * ns0, (size_t)3 * ns1, c->swaps.sendproc[w], c->swaps.sendproc[w + 1],
                          c->recvbuf.as<T>(), (size_t)3 * nr0, (size_t)3 * nr1, c->swaps.recvproc[w], c->swaps.recvproc[w + 1]));
-        if (zero_ghost_f) LAUNCH(c, (halo_unpack_x_pair_kernel<T, 1>), div_up(nr0 + nr1, TPB), TPB, c->x.as<V>(), c->f.as<V>(), c->sw[w].firstrecv, nr0, c->sw[w + 1].firstrecv, nr1, c->recvbuf.as<T>());
-        else LAUNCH(c, (halo_unpack_x_pair_kernel<T, 0>), div_up(nr0 + nr1, TPB), TPB, c->x.as<V>(), c->f.as<V>(), c->sw[w].firstrecv, nr0, c->sw[w + 1].firstrecv, nr1, c->recvbuf.as<T>());
+        if (zero_ghost_f) LAUNCH(c, (halo_unpack_x_pair_kernel<T, 1>), div_up(nr0 + nr1, TPB), TPB, c->x.as<V>(), c->f.as<V>(), c->sw[w].firstrecv, nr0, c->sw[w + 1].firstrecv, nr1, c->recvbuf.as<T>(), live_mirror(c));
+        else LAUNCH(c, (halo_unpack_x_pair_kernel<T, 0>), div_up(nr0 + nr1, TPB), TPB, c->x.as<V>(), c->f.as<V>(), c->sw[w].firstrecv, nr0, c->sw[w + 1].firstrecv, nr1, c->recvbuf.as<T>(), live_mirror(c));
 #else
         return set_err(MMD_ERR_STATE, "remote swap but library built without NCCL");
 #endif
@@ -1189,6 +1243,7 @@ template <class T> struct Impl {
   static int borders(mmd_ctx* c) {
     if (!c->have_comm || !c->have_box) return set_err(MMD_ERR_STATE, "borders: mmd_comm_setup / mmd_atom_set_box missing");
     c->nghost = 0;
+    c->xs_valid = false;
     const T px = (T)c->prd[0], py = (T)c->prd[1], pz = (T)c->prd[2];
     int w = 0;
     for (int dim = 0; dim < 3; dim++) {
@@ -1580,7 +1635,7 @@ int mmd_ctx_destroy(mmd_ctx* c) {
                     &c->eam_rho_der, &c->eam_z2_val, &c->eam_z2_der, &c->eam_frho_val, &c->eam_frho_der, &c->eam_cut,
                     &c->rho, &c->fp, &c->border_tiles, &c->sendbuf, &c->recvbuf, &c->exch_flag, &c->exch_pos,
                     &c->exch_holes, &c->ghost_src, &c->ghost_shift, &c->sruns, &c->tile_runs, &c->tile_center, &c->tile_info, &c->tile_slots, &c->tile_oslot, &c->trows,
-                    &c->tnum, &c->trowsq};
+                    &c->tnum, &c->trowsq, &c->xs_rec[0], &c->xs_rec[1], &c->xs_z[0], &c->xs_z[1], &c->slot_of, &c->xs_types};
   for (DevBuf* b : bufs) b->release();
   for (int w = 0; w < MMD_MAX_SWAPS; w++) c->sw[w].list.release();
   for (int r = 0; r < (int)c->peer_win.size(); r++)

@@ -23,6 +23,7 @@
 // reference's (ref/force_lj.cpp:185-263 half, :366-449 full), forces/energy/virial agree up to summation order.
 #pragma once
 #include "tile_kernels.cuh"
+#include "xs_mirror.cuh"
 
 namespace mmd {
 
@@ -116,31 +117,38 @@ tile_rows_deal_kernel(const unsigned short* __restrict__ rows, const int2* __res
 }
 
 // ---------------------------------------------------------------------------------------
-// Shared-memory image of a halo window for the dealt-row kernels.
+// Shared-memory image of a halo window for the dealt-row kernels (record formats: xs_mirror.cuh).
 //   FP64: rec[hcap] = (x,y) 16-byte records, z[hcap]; types (per-type parameter tables only) in st[hcap]
 //   FP32: rec[hcap] = (x,y,z,type bits) 16-byte records
-// followed by the run tables and a per-warp stash of 32 finished forces (the Verlet / store epilogue runs one lane
-// per atom).
+// followed by the CTA's force stash (one finished force per row of the tile: the store / Verlet epilogue runs one thread
+// per atom after all rows are done), the centre-pencil tables and the mbarrier of the bulk copies.
 // ---------------------------------------------------------------------------------------
-template <class T> struct QRec;
-template <> struct alignas(16) QRec<double> { double x, y; };
-template <> struct alignas(16) QRec<float> { float x, y, z, w; };
-
 template <class T> struct QWin {
   QRec<T>* rec;
   T* z;                // FP64 only
+  T* stash_f;          // [scap][3]
+  int* stash_a;        // [scap] tile-local index | centre pencil << 16
+  int4* pc;            // [16] centre pencils: {first tile-local index, atoms, first row, CSR slot of tile-local index 0}
+  int* pp;             // [17] exclusive prefix of the pencils' pass counts
   int* run_start;      // [TILE_MAXRUN]
   int* run_off;        // [TILE_MAXRUN + 1]
-  T* stash;            // [warps][32][3]
+  unsigned long long* bar;
   unsigned char* st;   // FP64 + per-type tables only
-  __device__ __forceinline__ void carve(unsigned char* base, int hcap, int nwarps) {
+  __device__ __forceinline__ void carve(unsigned char* base, int hcap, int scap) {
     rec = reinterpret_cast<QRec<T>*>(base);
     unsigned char* q = base + (size_t)hcap * 16;
     z = reinterpret_cast<T*>(q);
     if (sizeof(T) == 8) q += (size_t)hcap * 8;
-    stash = reinterpret_cast<T*>(q);
-    q += (size_t)nwarps * 96 * sizeof(T);
-    run_start = reinterpret_cast<int*>(q);
+    pc = reinterpret_cast<int4*>(q);
+    q += TILE_NCENTER * sizeof(int4);
+    bar = reinterpret_cast<unsigned long long*>(q);
+    q += 16;
+    stash_f = reinterpret_cast<T*>(q);
+    q += (size_t)scap * 3 * sizeof(T);
+    stash_a = reinterpret_cast<int*>(q);
+    q += (size_t)scap * sizeof(int);
+    pp = reinterpret_cast<int*>(q);
+    run_start = pp + 20;
     run_off = run_start + TILE_MAXRUN;
     st = reinterpret_cast<unsigned char*>(run_off + TILE_MAXRUN + 1);
   }
@@ -167,29 +175,40 @@ template <class T> struct QWin {
     else { zz = r.z; type = lane_to_type(r.w); }
   }
 };
-template <class T> __host__ __device__ inline size_t qwin_smem_bytes(int hcap, bool with_types, int nwarps = TILE_THREADS / 32) {
-  return (size_t)hcap * (sizeof(T) == 8 ? 24 : 16) + (size_t)nwarps * 96 * sizeof(T) + (2 * TILE_MAXRUN + 1) * sizeof(int) +
-         ((with_types && sizeof(T) == 8) ? (size_t)hcap : 0) + 16;
+template <class T> __host__ __device__ inline size_t qwin_smem_bytes(int hcap, bool with_types, int scap) {
+  return (size_t)hcap * (sizeof(T) == 8 ? 24 : 16) + TILE_NCENTER * sizeof(int4) + 16 + (size_t)scap * (3 * sizeof(T) + sizeof(int)) +
+         (20 + 2 * TILE_MAXRUN + 1) * sizeof(int) + ((with_types && sizeof(T) == 8) ? (size_t)hcap : 0) + 16;
 }
 
-template <class T, bool TYPES>
-__device__ __forceinline__ void qwin_stage(QWin<T>& S, const TileGeo& g, int t, int h, const int2* __restrict__ tile_runs,
-                                           const int* __restrict__ slots, const Vec4<T>* __restrict__ x) {
-  const int2* tr = tile_runs + (size_t)t * g.nrun;
-  for (int p = threadIdx.x; p < g.nrun; p += blockDim.x) {
-    const int2 r = tr[p];
-    S.run_start[p] = r.x;
-    S.run_off[p] = r.y;
-  }
-  if (threadIdx.x == 0) S.run_off[g.nrun] = h;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int p = w; p < g.nrun; p += nw) {
-    const int start = S.run_start[p], off = S.run_off[p], len = S.run_off[p + 1] - off;
-    for (int k = lane; k < len; k += 32) S.put(off + k, ldg4(x + __ldg(slots + start + k)), TYPES);
-  }
-  __syncthreads();
+// ---- asynchronous staging primitives (sm_90+): mbarrier + bulk copy (TMA engine, SASS UBLKCP) + cp.async (LDGSTS) ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// global -> shared bulk copy, completion counted in bytes on the mbarrier; dst, src and bytes are multiples of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // one 64-bit row word = the entries of four consecutive groups; the L2::128B hint pulls the atom's next block too
 __device__ __forceinline__ unsigned long long ldg_rowq(const unsigned long long* p) {
@@ -262,151 +281,203 @@ __device__ __forceinline__ void lj_pair(const QWin<T>& S, const LJDealtParams<T>
   }
 }
 
-// INTEG = 1: the velocity-Verlet halves that follow the force ride in the epilogue (see VerletParams, tile_kernels.cuh)
+// INTEG = 1: the velocity-Verlet halves that follow the force ride in the epilogue (see VerletParams, tile_kernels.cuh):
+// new positions go to x_out[] AND to the other buffer of the slot-ordered mirror (xs_out), which the next launch stages.
+//
+// Phases of a CTA (one tile):
+//   1. thread p < nrun issues ONE bulk copy for pencil run p of the halo window (mirror -> shared memory, 16-byte
+//      records); FP64 z values follow as 8-byte cp.async.  Row words of the first passes are requested meanwhile.
+//   2. passes of 4 atoms (a quarter warp each), dealt round robin over the 16 warps from the concatenated pass list of
+//      the tile's 16 centre pencils; finished forces go to the CTA's stash.
+//   3. epilogue with one thread per atom: store f, or finalIntegrate(n) + initialIntegrate(n+1) (ref/integrate.cpp:46-68).
 template <class T, int EV, int UNIFORM, int INTEG>
 __global__ void __launch_bounds__(TILE_THREADS, 2)
 force_lj_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, TileGeo g, const int2* __restrict__ tile_runs,
-                      const int4* __restrict__ tile_center, const int2* __restrict__ tile_info, const int* __restrict__ slots,
-                      const unsigned long long* __restrict__ rowsq, const int2* __restrict__ row_atom, int tcapq, int nlocal,
-                      LJDealtParams<T> P, VerletParams<T> VP, double* __restrict__ ev_out) {
+                      const int4* __restrict__ tile_center, const int2* __restrict__ tile_info, XsMirror<T> xs_in,
+                      const unsigned char* __restrict__ types_s, const unsigned long long* __restrict__ rowsq,
+                      const int2* __restrict__ row_atom, int tcapq, int nlocal, int scap, LJDealtParams<T> P,
+                      VerletParams<T> VP, XsMirror<T> xs_out, double* __restrict__ ev_out) {
   extern __shared__ __align__(16) unsigned char tile_smem_raw[];
   const int t = blockIdx.x;
   const int2 inf = tile_info[t];
   if (inf.y == 0) return;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
   const int p = lane & (QL - 1), qg = lane >> 3;
   const int wpr = tcapq / QB;  // 64-bit words per row
+  const int H = inf.x;
   const unsigned long long sent4 = 0x0001000100010001ull * (unsigned long long)(g.hcap - 1);
 
-  // {atom id, row length} and the first row word of a pass are fetched one pass ahead; the very first fetch is issued
-  // before the halo window is staged
-  int cr = w;
-  int4 ce = make_int4(0, 0, 0, 0);
-  if (cr < TILE_NCENTER) ce = tile_center[(size_t)t * TILE_NCENTER + cr];
-  int2 ta_n = make_int2(-1, 0);
-  unsigned long long w_n = sent4;
-  if (ce.x + qg < ce.y) {
-    const size_t q = (size_t)(ce.z + qg);
-    ta_n = __ldg(row_atom + q);
-    w_n = ldg_rowq(rowsq + q * wpr + p);
-  }
-
   QWin<T> S;
-  S.carve(tile_smem_raw, g.hcap, nw);
-  if (threadIdx.x == 0) {
+  S.carve(tile_smem_raw, g.hcap, scap);
+
+  // ---- phase 1: tables, then the asynchronous copies ----
+  const int2* tr = tile_runs + (size_t)t * g.nrun;
+  int2 my_run = make_int2(0, 0);
+  int my_len = 0;
+  if (tid < g.nrun) {
+    my_run = __ldg(tr + tid);
+    my_len = (tid + 1 < g.nrun ? __ldg(tr + tid + 1).y : H) - my_run.y;
+    S.run_start[tid] = my_run.x;
+    S.run_off[tid] = my_run.y;
+  }
+  if (tid == 0) {
+    S.run_off[g.nrun] = H;
+    mbar_init(S.bar, 1);
     Vec4<T> far;
     far.x = far.y = far.z = sentinel_coord<T>();
     far.w = type_to_lane<T>(0);
     S.put(g.hcap - 1, far, !UNIFORM);
   }
-  qwin_stage<T, !UNIFORM>(S, g, t, inf.x, tile_runs, slots, x);
-  T* stash = S.stash + w * 96;
-
-  double eng = 0.0, vir = 0.0, ke = 0.0;
-  for (; cr < TILE_NCENTER; cr += nw) {
-    if (cr != w) {  // only when the block has fewer warps than centre pencils
-      ce = tile_center[(size_t)t * TILE_NCENTER + cr];
-      ta_n = make_int2(-1, 0);
-      w_n = sent4;
-      if (ce.x + qg < ce.y) {
-        const size_t q = (size_t)(ce.z + qg);
-        ta_n = __ldg(row_atom + q);
-        w_n = ldg_rowq(rowsq + q * wpr + p);
+  if (w == 0) {  // centre pencils: lanes 0..15
+    int4 ce = make_int4(0, 0, 0, 0);
+    int slot0 = 0;
+    if (lane < TILE_NCENTER) {
+      ce = __ldg(tile_center + (size_t)t * TILE_NCENTER + lane);
+      const int2 r = __ldg(tr + (lane % TBY + g.sy) + (lane / TBY + g.sz) * g.nry);
+      slot0 = r.x - r.y;
+    }
+    const int n = ce.y - ce.x;
+    const int np = (n + 3) >> 2;
+    int incl = np;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane < TILE_NCENTER) {
+      S.pc[lane] = make_int4(ce.x, n, ce.z, slot0);
+      S.pp[lane] = incl - np;
+    }
+    if (lane == TILE_NCENTER) S.pp[TILE_NCENTER] = incl;  // lanes >= 16 add nothing: incl = total
+  }
+  __syncthreads();
+  if (tid == 0) mbar_expect_tx(S.bar, (unsigned)H * 16u);
+  if (my_len > 0) bulk_g2s(S.rec + my_run.y, xs_in.rec + my_run.x, (unsigned)my_len * 16u, S.bar);
+  if constexpr (sizeof(T) == 8) {
+    for (int r = w; r < g.nrun; r += nw) {
+      const int start = S.run_start[r], off = S.run_off[r], len = S.run_off[r + 1] - off;
+      for (int k = lane; k < len; k += 32) {
+        cp_async8(S.z + off + k, xs_in.z + start + k);
+        if (!UNIFORM) S.st[off + k] = __ldg(types_s + start + k);
       }
     }
-    for (int a0 = ce.x; a0 < ce.y; a0 += 32) {
-      const int npass = (min(32, ce.y - a0) + 3) >> 2;
-      for (int ps = 0; ps < npass; ps++) {
-        const int a = a0 + ps * 4 + qg;
-        const bool have = a < ce.y;
-        const int2 ta = ta_n;
-        // an atom owns its row whatever the row's length (an isolated atom has an empty one and still integrates)
-        const bool own = have && ta.x >= 0 && ta.x < nlocal;
-        const int n = own ? max(ta.y, 0) : 0;
-        const int aa = have ? a : ce.x;
-        const int G = (n + QL - 1) / QL;          // groups of this atom's row
-        const int nwords = (G + QB - 1) / QB;     // row words that hold them; beyond: all-sentinel words
-        const unsigned long long* __restrict__ rowq = rowsq + (size_t)(ce.z + (aa - ce.x)) * wpr + p;
-        unsigned long long w0 = nwords > 0 ? w_n : sent4;
-        unsigned long long w1 = sent4;
-        if (nwords > 1) w1 = ldg_rowq(rowq + QL);
-        {  // next pass
-          const int an = a + 4;
-          ta_n = make_int2(-1, 0);
-          w_n = sent4;
-          if (an < ce.y) {
-            const size_t q = (size_t)(ce.z + (an - ce.x));
-            ta_n = __ldg(row_atom + q);
-            w_n = ldg_rowq(rowsq + q * wpr + p);
-          }
-        }
-        const int gmax = __reduce_max_sync(0xffffffffu, G);   // the quarter warps of a pass run in lock step
-        T xi, yi, zi;
-        int ti = 0;
-        if (UNIFORM) S.get(aa, xi, yi, zi); else S.get(aa, xi, yi, zi, ti);
-        T fx = 0, fy = 0, fz = 0;
-        const int nfull = gmax >> 2;
-        for (int b = 0; b < nfull; b++) {
-          const unsigned long long cur = w0;
-          w0 = w1;
-          w1 = sent4;
-          if (b + 2 < nwords) w1 = ldg_rowq(rowq + (size_t)(b + 2) * QL);
-          // four independent pair evaluations in flight: the FP64 dependency chains overlap
+  }
+
+  // pass list: pass i of the tile belongs to the pencil c with pp[c] <= i < pp[c+1]
+  const int NP = S.pp[TILE_NCENTER];
+  const int my_end = lane < TILE_NCENTER ? S.pp[lane + 1] : 0x7fffffff;
+  const int qtile0 = S.pc[0].z;
+  int2 ta_n = make_int2(-1, 0);
+  unsigned long long w_n = sent4;
+  int a_n = 0, q_n = 0, c_n = 0;
+  bool have_n = false;
+  auto locate = [&](int i) {  // fills the *_n state for pass i (warp-uniform i)
+    c_n = __popc(__ballot_sync(0xffffffffu, my_end <= i));
+    have_n = false;
+    ta_n = make_int2(-1, 0);
+    w_n = sent4;
+    if (i < NP) {
+      const int4 pc = S.pc[c_n];
+      const int k = (i - S.pp[c_n]) * 4 + qg;
+      have_n = k < pc.y;
+      a_n = pc.x + (have_n ? k : 0);
+      q_n = pc.z + (have_n ? k : 0);
+      if (have_n) {
+        ta_n = __ldg(row_atom + q_n);
+        w_n = ldg_rowq(rowsq + (size_t)q_n * wpr + p);
+      }
+    }
+  };
+  locate(w);
+
+  if constexpr (sizeof(T) == 8) cp_async_wait_all();
+  mbar_wait(S.bar, 0);
+  __syncthreads();
+
+  // ---- phase 2: the passes ----
+  double eng = 0.0, vir = 0.0, ke = 0.0;
+  for (int i = w; i < NP; i += nw) {
+    const bool have = have_n;
+    const int a = a_n, q = q_n, c = c_n;
+    const int2 ta = ta_n;
+    // an atom owns its row whatever the row's length (an isolated atom has an empty one and still integrates)
+    const bool own = have && ta.x >= 0 && ta.x < nlocal;
+    const int n = own ? max(ta.y, 0) : 0;
+    const int G = (n + QL - 1) / QL;          // groups of this atom's row
+    const int nwords = (G + QB - 1) / QB;     // row words that hold them; beyond: all-sentinel words
+    const unsigned long long* __restrict__ rowq = rowsq + (size_t)q * wpr + p;
+    unsigned long long w0 = nwords > 0 ? w_n : sent4;
+    unsigned long long w1 = sent4;
+    if (nwords > 1) w1 = ldg_rowq(rowq + QL);
+    if (INTEG && own && p == 1) prefetch_l2(VP.v + ta.x);
+    locate(i + nw);  // next pass of this warp
+    const int gmax = __reduce_max_sync(0xffffffffu, G);   // the quarter warps of a pass run in lock step
+    T xi, yi, zi;
+    int ti = 0;
+    if (UNIFORM) S.get(a, xi, yi, zi); else S.get(a, xi, yi, zi, ti);
+    T fx = 0, fy = 0, fz = 0;
+    const int nfull = gmax >> 2;
+    for (int b = 0; b < nfull; b++) {
+      const unsigned long long cur = w0;
+      w0 = w1;
+      w1 = sent4;
+      if (b + 2 < nwords) w1 = ldg_rowq(rowq + (size_t)(b + 2) * QL);
+      // four independent pair evaluations in flight: the FP64 dependency chains overlap
 #pragma unroll
-          for (int e = 0; e < QB; e++)
-            lj_pair<T, EV, UNIFORM>(S, P, (int)((cur >> (16 * e)) & 0xffffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
-        }
-        if (gmax & 2) {
-          lj_pair<T, EV, UNIFORM>(S, P, (int)(w0 & 0xffffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
-          lj_pair<T, EV, UNIFORM>(S, P, (int)((w0 >> 16) & 0xffffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
-        }
-        if (gmax & 1)
-          lj_pair<T, EV, UNIFORM>(S, P, (int)((w0 >> ((gmax & 2) * 16)) & 0xffffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
-        fx = group_sum<QL>(fx);
-        fy = group_sum<QL>(fy);
-        fz = group_sum<QL>(fz);
-        if (p == 0) {
-          T* s = stash + (ps * 4 + qg) * 3;
-          s[0] = fx; s[1] = fy; s[2] = fz;
-        }
-      }
-      __syncwarp();
-      // ---- epilogue: one lane per atom of this block of 32 ----
-      {
-        const int a = a0 + lane;
-        int id = -1;
-        if (a < ce.y) {
-          const int2 ta = __ldg(row_atom + (size_t)(ce.z + (a - ce.x)));
-          if (ta.x >= 0 && ta.x < nlocal) id = ta.x;
-        }
-        if (id >= 0) {
-          const T fxa = stash[lane * 3 + 0], fya = stash[lane * 3 + 1], fza = stash[lane * 3 + 2];
-          if (INTEG) {
-            T xa, ya, za;
-            S.get(a, xa, ya, za);
-            Vec4<T> vi = VP.v[id];
-            vi.x += VP.dtforce * fxa;
-            vi.y += VP.dtforce * fya;
-            vi.z += VP.dtforce * fza;
-            if (EV) ke += (double)((vi.x * vi.x + vi.y * vi.y + vi.z * vi.z) * VP.mass);
-            vi.x += VP.dtforce * fxa;
-            vi.y += VP.dtforce * fya;
-            vi.z += VP.dtforce * fza;
-            Vec4<T> xo;
-            xo.x = xa + VP.dt * vi.x;
-            xo.y = ya + VP.dt * vi.y;
-            xo.z = za + VP.dt * vi.z;
-            xo.w = x[id].w;  // the type lane travels with the atom
-            VP.v[id] = vi;
-            VP.x_out[id] = xo;
-          } else {
-            Vec4<T> out;
-            out.x = fxa; out.y = fya; out.z = fza; out.w = (T)0;
-            f[id] = out;
-          }
-        }
-      }
-      __syncwarp();
+      for (int e = 0; e < QB; e++)
+        lj_pair<T, EV, UNIFORM>(S, P, (int)((cur >> (16 * e)) & 0xffffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
+    }
+    if (gmax & 2) {
+      lj_pair<T, EV, UNIFORM>(S, P, (int)(w0 & 0xffffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
+      lj_pair<T, EV, UNIFORM>(S, P, (int)((w0 >> 16) & 0xffffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
+    }
+    if (gmax & 1)
+      lj_pair<T, EV, UNIFORM>(S, P, (int)((w0 >> ((gmax & 2) * 16)) & 0xffffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
+    fx = group_sum<QL>(fx);
+    fy = group_sum<QL>(fy);
+    fz = group_sum<QL>(fz);
+    if (p == 0 && have) {
+      const int j = q - qtile0;
+      T* s = S.stash_f + j * 3;
+      s[0] = fx; s[1] = fy; s[2] = fz;
+      S.stash_a[j] = a | (c << 16);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3: one thread per row of the tile ----
+  const int nrows = S.pc[TILE_NCENTER - 1].z + S.pc[TILE_NCENTER - 1].y - qtile0;
+  for (int j = tid; j < nrows; j += blockDim.x) {
+    const int2 ta = __ldg(row_atom + (size_t)(qtile0 + j));
+    if (ta.x < 0 || ta.x >= nlocal) continue;
+    const int id = ta.x;
+    const T fxa = S.stash_f[j * 3 + 0], fya = S.stash_f[j * 3 + 1], fza = S.stash_f[j * 3 + 2];
+    if (INTEG) {
+      const int ac = S.stash_a[j];
+      const int a = ac & 0xffff;
+      T xa, ya, za;
+      S.get(a, xa, ya, za);
+      Vec4<T> vi = VP.v[id];
+      vi.x += VP.dtforce * fxa;
+      vi.y += VP.dtforce * fya;
+      vi.z += VP.dtforce * fza;
+      if (EV) ke += (double)((vi.x * vi.x + vi.y * vi.y + vi.z * vi.z) * VP.mass);
+      vi.x += VP.dtforce * fxa;
+      vi.y += VP.dtforce * fya;
+      vi.z += VP.dtforce * fza;
+      Vec4<T> xo;
+      xo.x = xa + VP.dt * vi.x;
+      xo.y = ya + VP.dt * vi.y;
+      xo.z = za + VP.dt * vi.z;
+      if constexpr (sizeof(T) == 8) xo.w = x[id].w;  // the type lane travels with the atom
+      else xo.w = S.rec[a].w;
+      VP.v[id] = vi;
+      VP.x_out[id] = xo;
+      xs_out.put_slot(S.pc[ac >> 16].w + a, xo);
+    } else {
+      Vec4<T> out;
+      out.x = fxa; out.y = fya; out.z = fza; out.w = (T)0;
+      f[id] = out;
     }
   }
   if (EV) {

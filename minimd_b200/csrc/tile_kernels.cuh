@@ -56,7 +56,7 @@ __device__ __forceinline__ int tile_bin_id(const TileGeo& g, int x, int y, int z
 __global__ void __launch_bounds__(128)
 tile_table_kernel(TileGeo g, const int* __restrict__ bin_start, const int* __restrict__ bin_atoms, int mbins, int nlocal,
                   int2* __restrict__ runs, int4* __restrict__ center, int2* __restrict__ info, int* __restrict__ max_h,
-                  int* __restrict__ row_counter) {
+                  int* __restrict__ row_counter, int* __restrict__ max_rows) {
   __shared__ int s_start[4][TILE_MAXRUN + 1];
   __shared__ int s_off[4][TILE_MAXRUN + 1];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -122,7 +122,10 @@ tile_table_kernel(TileGeo g, const int* __restrict__ bin_start, const int* __res
   }
   const int tile_rows = __shfl_sync(0xffffffffu, incl, 31);
   int base = 0;
-  if (lane == 0 && any) base = atomicAdd(row_counter, tile_rows);
+  if (lane == 0 && any) {
+    base = atomicAdd(row_counter, tile_rows);
+    atomicMax(max_rows, tile_rows);
+  }
   base = __shfl_sync(0xffffffffu, base, 0);
   if (lane < TILE_NCENTER) center[(size_t)t * TILE_NCENTER + lane] = make_int4(lo, hi, any ? base + incl - len_c : 0, 0);
   if (lane == 0) {
