@@ -21,6 +21,7 @@
 #include "scan.cuh"
 #include "tile_kernels.cuh"
 #include "tile_dealt_kernels.cuh"
+#include "tile_build_lane.cuh"
 #include "tile_eam_kernels.cuh"
 
 #ifdef MMD_WITH_NCCL
@@ -163,7 +164,8 @@ struct mmd_ctx {
   TileGeo tgeo;
   int nsruns = 0;           // runs of the symmetric (full) stencil
   DevBuf sruns, tile_runs, tile_center, tile_info, tile_slots, tile_oslot, trows, tnum;
-  bool tile_xsort = true;     // option "tile_xsort": x-sorted windows + interval build (neigh_build_tile3_kernel)
+  bool tile_xsort = true;     // option "tile_xsort": x-sorted windows + interval build
+  bool tile_lane_build = false;  // option "tile_lane_build": interval build with one lane per atom (default 0: one warp per atom, measured faster)
   bool list_xsorted = false;  // the current list was built on x-sorted windows
   int tcap = 0;             // row capacity (16-bit entries, multiple of 8)
   int tcap_floor = 0;       // raised when a build overflowed its rows
@@ -604,7 +606,7 @@ template <class T> struct Impl {
       c->tile_fallbacks++;
       return MMD_OK;  // *done stays false
     }
-    g.hcap = std::max(64, (c->tile_max_h + 1 + 63) & ~63);  // + 1: the build's sentinel slot
+    g.hcap = std::max(64, (c->tile_max_h + 8 + 63) & ~63);  // + 8: sentinel slots of the builds / the dealt force kernel
     Build2Params<T> B;
     {
       const std::vector<double>& cuts = c->h_cutneighsq;  // host copy kept by mmd_neigh_setup (values exact in T)
@@ -646,7 +648,30 @@ template <class T> struct Impl {
       c->cutneighsq.as<T>(), c->ntypes, g, B, c->tile_runs.as<int2>(), c->tile_center.as<int4>(), c->tile_info.as<int2>(),  \
       c->trows.as<unsigned short>(), c->tcap, c->numneigh.as<int>(), c->tnum.as<int2>(), c->d_scal + 12, c->d_scal + 1,    \
       c->d_scal + 10, c->d_total
-      if (xsorted) {
+      if (xsorted && c->tile_lane_build && buildl_smem_bytes<T>(g, g.hcap, !B.uniform_cut) <= (size_t)(227 * 1024 - 2048)) {
+        const size_t bl_smem = buildl_smem_bytes<T>(g, g.hcap, !B.uniform_cut);
+#define NBL_ARGS                                                                                                          \
+  c->x.as<V>(), c->nlocal, c->bin_start.as<int>(), c->tile_slots.as<int>(), c->mbins, c->sruns.as<StencilRun>(), c->nsruns, \
+      c->cutneighsq.as<T>(), c->ntypes, g, B, c->tile_runs.as<int2>(), c->tile_center.as<int4>(), c->tile_info.as<int2>(),  \
+      c->trows.as<unsigned short>(), c->tcap, c->numneigh.as<int>(), c->tnum.as<int2>(), c->d_scal + 12, c->d_scal + 1,    \
+      c->d_scal + 10, c->d_total
+#define NBL_LAUNCH(M, U)                                                                       \
+  do {                                                                                         \
+    MM(smem_optin(c, neigh_build_lane_kernel<T, M, U>));                                       \
+    LAUNCH_SMEM(c, (neigh_build_lane_kernel<T, M, U>), g.ntiles, TBL_THREADS, bl_smem, NBL_ARGS); \
+  } while (0)
+        if (B.uniform_cut) {
+          if (mode == 0) NBL_LAUNCH(0, 1);
+          if (mode == 1) NBL_LAUNCH(1, 1);
+          if (mode == 2) NBL_LAUNCH(2, 1);
+        } else {
+          if (mode == 0) NBL_LAUNCH(0, 0);
+          if (mode == 1) NBL_LAUNCH(1, 0);
+          if (mode == 2) NBL_LAUNCH(2, 0);
+        }
+#undef NBL_LAUNCH
+#undef NBL_ARGS
+      } else if (xsorted) {
         const size_t b3_smem = build3_smem_bytes<T>(g, g.hcap, !B.uniform_cut);
         MM(smem_optin(c, neigh_build_tile3_kernel<T, 0, 1>)); MM(smem_optin(c, neigh_build_tile3_kernel<T, 1, 1>));
         MM(smem_optin(c, neigh_build_tile3_kernel<T, 2, 1>)); MM(smem_optin(c, neigh_build_tile3_kernel<T, 0, 0>));
@@ -715,12 +740,12 @@ template <class T> struct Impl {
     if (c->tile_dealt && !c->have_eam) {
       const int nrows = std::max(nall, 1);
       c->tcapq = dealt_capacity(std::min(c->tile_max_full, c->tcap));
-      const size_t dsm = deal_smem_bytes(c->tcapq);
-      if (dsm <= (size_t)(227 * 1024 - 2048)) {
+      const size_t dsm = deal_smem_bytes(c->tcap, c->tcapq);
+      if (dsm <= (size_t)(227 * 1024 - 2048) && c->tcapq <= (DEAL_MAXROW & ~31)) {
         MM(c->trowsq.reserve((size_t)nrows * c->tcapq * sizeof(unsigned short) + 256, c->stream, 0, 1.05));
         MM(smem_optin(c, tile_rows_deal_kernel));
         LAUNCH_SMEM(c, tile_rows_deal_kernel, div_up(nrows, DEAL_THREADS), DEAL_THREADS, dsm, c->trows.as<unsigned short>(),
-                    c->tnum.as<int2>(), nrows, c->tcap, c->nlocal, c->trowsq.as<unsigned short>(), c->tcapq, g.hcap - 1);
+                    c->tnum.as<int2>(), nrows, c->tcap, c->nlocal, c->trowsq.as<unsigned short>(), c->tcapq, g.hcap - 8);
         c->list_dealt = true;
         c->xs_valid = false;
         MM(xs_fill(c));
@@ -2123,6 +2148,8 @@ int mmd_set_option(mmd_ctx* c, const char* key, long long value) {
     if (!c->fuse_halo) c->ghosts_resolved = false;
   } else if (k == "tile_dealt") {  // 1: the LJ force kernel walks bank-dealt rows (quarter warp per atom); 0: one lane pair per row
     c->tile_dealt = value != 0;     // takes effect at the next neighbor build
+  } else if (k == "tile_lane_build") {
+    c->tile_lane_build = value != 0;
   } else if (k == "tile_xsort") {
     c->tile_xsort = value != 0;
   } else if (k == "tile_eam") {

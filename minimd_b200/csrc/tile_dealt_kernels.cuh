@@ -14,10 +14,11 @@
 //
 // Storage: entry (group g, lane p) of a row is the 16-bit word (g>>2)*32 + p*4 + (g&3): lane p fetches the entries of
 // four consecutive groups with one 64-bit load, a quarter warp reads 64 contiguous bytes.  Rows are tcapq entries long
-// (a multiple of 32).  An entry is the plain tile-local index (the half-list flag of the build's rows is not needed by
-// the force); every slot that holds no neighbor -- (g,p) with g >= G or p*G + g >= n, up to the end of the row's last
-// 64-byte block -- holds the SENTINEL index hcap-1, a shared-memory slot the force kernel fills with a far-away position:
-// the pair loop carries no validity logic at all, a sentinel pair simply fails the cutoff test.
+// (a multiple of 32).  An entry is the tile-local index with the build's half-list flag in bit 15 (the force kernels
+// mask it off, the export and the counters use it); every slot that holds no neighbor -- (g,p) with g >= G or
+// p*G + g >= n, up to the end of the row's last 64-byte block -- holds a SENTINEL index (hcap-8+p), shared-memory slots
+// the force kernel fills with a far-away position: the pair loop carries no validity logic at all, a sentinel pair
+// simply fails the cutoff test.
 //
 // The kernel evaluates every atom's complete neighborhood ("owner computes", as tile_kernels.cuh): the pair set is the
 // reference's (ref/force_lj.cpp:185-263 half, :366-449 full), forces/energy/virial agree up to summation order.
@@ -34,23 +35,27 @@ constexpr int QBLK = QL * QB;    // entries per row block (64 bytes)
 __host__ __device__ inline int dealt_capacity(int longest_row) { return ((longest_row > 1 ? longest_row : 1) + QBLK - 1) / QBLK * QBLK; }
 
 // ---------------------------------------------------------------------------------------
-// rows in candidate order (neigh_build_tile*_kernel) -> bank-dealt rows.  One thread per row: count the 8 classes,
-// then place every entry at its dealt position inside a shared-memory copy of the row (odd word stride: the threads'
-// scattered 16-bit stores spread over the banks); the CTA writes the rows out with 16-byte stores.
+// rows in candidate order (neigh_build_*_kernel) -> bank-dealt rows.  A CTA takes 128 consecutive rows: it copies them
+// into shared memory with coalesced 16-byte loads, then ONE THREAD PER ROW counts the 8 classes and places every entry
+// at its dealt position inside a second shared-memory copy (odd word strides: the threads' accesses spread over the
+// banks), and the CTA writes the dealt rows out with 16-byte stores.  Empty slots of a lane p hold the sentinel index
+// sentinel0 + p: hcap-8 .. hcap-1 are eight far-away atoms, one per bank class, so that a sentinel read by lane p (which
+// mostly holds entries of the classes around p) rarely collides with a real entry of its group.
 // ---------------------------------------------------------------------------------------
 constexpr int DEAL_THREADS = 128;
-__host__ __device__ inline size_t deal_smem_bytes(int tcapq) { return (size_t)DEAL_THREADS * (tcapq / 2 + 1) * 4 + DEAL_THREADS * 4; }
+constexpr int DEAL_MAXROW = 255;  // longest row the 8-bit class counters handle
+__host__ __device__ inline size_t deal_smem_bytes(int tcap, int tcapq) {
+  return (size_t)DEAL_THREADS * ((tcap / 2 + 1) + (tcapq / 2 + 1)) * 4 + DEAL_THREADS * 4;
+}
 
 __global__ void __launch_bounds__(DEAL_THREADS)
 tile_rows_deal_kernel(const unsigned short* __restrict__ rows, const int2* __restrict__ row_atom, int nrows, int tcap,
-                      int nlocal, unsigned short* __restrict__ rowsq, int tcapq, int sentinel) {
+                      int nlocal, unsigned short* __restrict__ rowsq, int tcapq, int sentinel0) {
   extern __shared__ __align__(16) unsigned char deal_smem[];
-  const int wstride = tcapq / 2 + 1;
-  unsigned* sw = reinterpret_cast<unsigned*>(deal_smem);
-  int* s_n = reinterpret_cast<int*>(sw + DEAL_THREADS * wstride);
-  const unsigned fill = (unsigned)sentinel | ((unsigned)sentinel << 16);
-  for (int k = threadIdx.x; k < DEAL_THREADS * wstride; k += DEAL_THREADS) sw[k] = fill;
-  __syncthreads();
+  const int sstride = tcap / 2 + 1, dstride = tcapq / 2 + 1;  // words per row, both odd
+  unsigned* s_src = reinterpret_cast<unsigned*>(deal_smem);
+  unsigned* s_dst = s_src + DEAL_THREADS * sstride;
+  int* s_n = reinterpret_cast<int*>(s_dst + DEAL_THREADS * dstride);
   const int q0 = blockIdx.x * DEAL_THREADS;
   const int q = q0 + threadIdx.x;
   int n = 0;
@@ -59,46 +64,54 @@ tile_rows_deal_kernel(const unsigned short* __restrict__ rows, const int2* __res
     if (ta.x >= 0 && ta.x < nlocal) n = min(min(max(ta.y, 0), tcap), tcapq);
   }
   s_n[threadIdx.x] = n;
-  if (n > 0) {
-    const unsigned short* __restrict__ src = rows + (size_t)q * tcap;
-    // class counts, 16 bits each: classes 0-3 in c0, 4-7 in c1
-    unsigned long long c0 = 0ull, c1 = 0ull;
-    for (int k = 0; k < n; k += 8) {
-      const uint4 v = *reinterpret_cast<const uint4*>(src + k);
-      const unsigned wds[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int e = 0; e < 8; e++) {
-        if (k + e < n) {
-          const unsigned ent = (wds[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
-          const unsigned long long inc = 1ull << ((ent & 3u) * 16u);
-          if (ent & 4u) c1 += inc; else c0 += inc;
-        }
+  // sentinel pattern of a dealt row: word k holds slots 2k, 2k+1 of lane (2k >> 2) & 7
+  for (int k = threadIdx.x; k < DEAL_THREADS * dstride; k += DEAL_THREADS) {
+    const int wd = k % dstride;
+    const unsigned sv = (unsigned)(sentinel0 + ((wd >> 1) & 7));
+    s_dst[k] = sv | (sv << 16);
+  }
+  __syncthreads();
+  {  // coalesced copy-in: 16 bytes per thread and step
+    const int cpr = tcap / 8;
+    for (int idx = threadIdx.x; idx < DEAL_THREADS * cpr; idx += DEAL_THREADS) {
+      const int r = idx / cpr, ch = idx - r * cpr;
+      if (ch * 8 < s_n[r]) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(rows + (size_t)(q0 + r) * tcap + ch * 8));
+        unsigned* d = s_src + r * sstride + ch * 4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
       }
     }
-    // exclusive prefix over the classes (lane k of the product = sum of the lanes below k; totals < 65536)
-    const unsigned long long tot0 = ((c0 * 0x0001000100010001ull) >> 48) & 0xffffull;
-    unsigned long long p0 = c0 * 0x0001000100010000ull;
-    unsigned long long p1 = c1 * 0x0001000100010000ull + tot0 * 0x0001000100010001ull;
+  }
+  __syncthreads();
+  if (n > 0) {
+    const unsigned short* __restrict__ src = reinterpret_cast<const unsigned short*>(s_src + threadIdx.x * sstride);
+    // class counts, 8 bits each (n <= 255): classes 0-3 in c0, 4-7 in c1
+    unsigned c0 = 0u, c1 = 0u;
+    for (int k = 0; k < n; k++) {
+      const unsigned ent = src[k];
+      const unsigned inc = 1u << ((ent & 3u) * 8u);
+      c0 += (ent & 4u) ? 0u : inc;
+      c1 += (ent & 4u) ? inc : 0u;
+    }
+    // exclusive prefix over the classes (byte k of the product = sum of the bytes below k; totals < 256)
+    const unsigned tot0 = (c0 * 0x01010101u) >> 24;
+    unsigned p0 = c0 * 0x01010100u;
+    unsigned p1 = c1 * 0x01010100u + tot0 * 0x01010101u;
     const int G = (n + QL - 1) / QL;
     const float rG = 1.0f / (float)G;
-    unsigned short* dst = reinterpret_cast<unsigned short*>(sw + threadIdx.x * wstride);
-    for (int k = 0; k < n; k += 8) {
-      const uint4 v = *reinterpret_cast<const uint4*>(src + k);
-      const unsigned wds[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int e = 0; e < 8; e++) {
-        if (k + e < n) {
-          const unsigned ent = (wds[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
-          const unsigned sh = (ent & 3u) * 16u;
-          int t;
-          if (ent & 4u) { t = (int)((p1 >> sh) & 0xffffull); p1 += 1ull << sh; }
-          else { t = (int)((p0 >> sh) & 0xffffull); p0 += 1ull << sh; }
-          // t / G for t < 65536: (t + 0.5) / G stays >= 0.5 / G away from every integer, far above the FP32 error
-          const int p = __float2int_rd(((float)t + 0.5f) * rG);
-          const int g = t - p * G;
-          dst[(g >> 2) * QBLK + p * QB + (g & 3)] = (unsigned short)(ent & 0x7fffu);
-        }
-      }
+    unsigned short* dst = reinterpret_cast<unsigned short*>(s_dst + threadIdx.x * dstride);
+    for (int k = 0; k < n; k++) {
+      const unsigned ent = src[k];
+      const unsigned sh = (ent & 3u) * 8u;
+      const bool hi = (ent & 4u) != 0u;
+      const int t = (int)(((hi ? p1 : p0) >> sh) & 0xffu);
+      const unsigned inc = 1u << sh;
+      p0 += hi ? 0u : inc;
+      p1 += hi ? inc : 0u;
+      // t / G for t < 256: (t + 0.5) / G stays >= 0.5 / G away from every integer, far above the FP32 error
+      const int p = __float2int_rd(((float)t + 0.5f) * rG);
+      const int g = t - p * G;
+      dst[(g >> 2) * QBLK + p * QB + (g & 3)] = (unsigned short)ent;   // the half-list flag (bit 15) travels along
     }
   }
   __syncthreads();
@@ -108,9 +121,9 @@ tile_rows_deal_kernel(const unsigned short* __restrict__ rows, const int2* __res
     const int r = idx / cpr, ch = idx - r * cpr;
     const int nr = s_n[r];
     if (ch * 8 < ((nr + QBLK - 1) / QBLK) * QBLK) {
-      const unsigned* s = sw + r * wstride + ch * 4;
+      const unsigned* sp = s_dst + r * dstride + ch * 4;
       uint4 o;
-      o.x = s[0]; o.y = s[1]; o.z = s[2]; o.w = s[3];
+      o.x = sp[0]; o.y = sp[1]; o.z = sp[2]; o.w = sp[3];
       *reinterpret_cast<uint4*>(rowsq + (size_t)(q0 + r) * tcapq + ch * 8) = o;
     }
   }
@@ -305,7 +318,7 @@ force_lj_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Ti
   const int p = lane & (QL - 1), qg = lane >> 3;
   const int wpr = tcapq / QB;  // 64-bit words per row
   const int H = inf.x;
-  const unsigned long long sent4 = 0x0001000100010001ull * (unsigned long long)(g.hcap - 1);
+  const unsigned long long sent4 = 0x0001000100010001ull * (unsigned long long)(g.hcap - 8 + p);  // lane p's sentinel
 
   QWin<T> S;
   S.carve(tile_smem_raw, g.hcap, scap);
@@ -323,10 +336,12 @@ force_lj_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Ti
   if (tid == 0) {
     S.run_off[g.nrun] = H;
     mbar_init(S.bar, 1);
+  }
+  if (tid >= 32 && tid < 40) {  // the eight sentinel atoms, one per bank class
     Vec4<T> far;
     far.x = far.y = far.z = sentinel_coord<T>();
     far.w = type_to_lane<T>(0);
-    S.put(g.hcap - 1, far, !UNIFORM);
+    S.put(g.hcap - 40 + tid, far, !UNIFORM);
   }
   if (w == 0) {  // centre pencils: lanes 0..15
     int4 ce = make_int4(0, 0, 0, 0);
@@ -425,14 +440,14 @@ force_lj_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Ti
       // four independent pair evaluations in flight: the FP64 dependency chains overlap
 #pragma unroll
       for (int e = 0; e < QB; e++)
-        lj_pair<T, EV, UNIFORM>(S, P, (int)((cur >> (16 * e)) & 0xffffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
+        lj_pair<T, EV, UNIFORM>(S, P, (int)((cur >> (16 * e)) & 0x7fffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
     }
     if (gmax & 2) {
-      lj_pair<T, EV, UNIFORM>(S, P, (int)(w0 & 0xffffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
-      lj_pair<T, EV, UNIFORM>(S, P, (int)((w0 >> 16) & 0xffffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
+      lj_pair<T, EV, UNIFORM>(S, P, (int)(w0 & 0x7fffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
+      lj_pair<T, EV, UNIFORM>(S, P, (int)((w0 >> 16) & 0x7fffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
     }
     if (gmax & 1)
-      lj_pair<T, EV, UNIFORM>(S, P, (int)((w0 >> ((gmax & 2) * 16)) & 0xffffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
+      lj_pair<T, EV, UNIFORM>(S, P, (int)((w0 >> ((gmax & 2) * 16)) & 0x7fffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
     fx = group_sum<QL>(fx);
     fy = group_sum<QL>(fy);
     fz = group_sum<QL>(fz);
