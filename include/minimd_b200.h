@@ -203,15 +203,23 @@ int mmd_query_int(mmd_ctx* ctx, const char* key, long long* value);
  *   "tile_lists" (1)   neighbor lists as 16-bit tile-local rows + shared-memory force kernels (LJ); 0 = classic rows of
  *                      global ids.  Takes effect at the next mmd_neigh_build.  mmd_neigh_download returns the reference's
  *                      rows in either case.
+ *   "tile_dealt" (1)   LJ on tile lists: the force kernel walks a bank-dealt copy of the rows (a quarter warp per atom,
+ *                      halo window staged by bulk asynchronous copies from a slot-ordered position mirror); 0 = one lane
+ *                      pair per row, window staged by an indexed gather.  Takes effect at the next mmd_neigh_build.
+ *   "tile_xsort" (1)   tile lists: every bin of the windows' private slot map sorted by x + interval build; 0 = windows in
+ *                      CSR order + per-bin candidate-table build
+ *   "tile_build2" (1)  0 = tile rows from the warp-per-bin build (no shared-memory window; testing / odd geometries)
+ *   "tile_lane_build" (0)  interval build with one lane per atom instead of one warp per atom (measured slower)
  *   "tile_eam" (0)     tile-resident lists for the EAM force too (measured slower than the classic kernels)
+ *   "force_nonuniform" (0)  testing: use the per-type parameter-table kernels even when all type pairs are equal
  *   "fuse_integrate" (1)  mmd_run: finalIntegrate(n) + initialIntegrate(n+1) in one kernel
  *   "fuse_force" (1)      mmd_run, tile lists: ... and both inside the force kernel's epilogue
  *   "fuse_halo" (1)       one rank: forward halo in one launch (ghosts resolved to their local source)
  *   "p2p_halo" (1)        several ranks: forward halo over CUDA-IPC peer windows; 0 = NCCL send/recv
  *   "lj_threads_per_atom" (0 = auto), "eam_threads_per_atom" (8): lanes per atom of the classic kernels
  *   "phase_timing" (0)    per-phase CUDA-event timing of mmd_run
- * Queries added by these paths: "list_tile", "tile_ok", "tile_builds", "tile_fallbacks", "tile_max_halo",
- * "tile_max_full", "tile_row_capacity", "tile_count", "p2p_active", "p2p_calls". */
+ * Queries added by these paths: "list_tile", "list_dealt", "list_xsorted", "tile_ok", "tile_builds", "tile_fallbacks",
+ * "tile_max_halo", "tile_max_full", "tile_row_capacity", "tile_dealt_capacity", "tile_count", "p2p_active", "p2p_calls". */
 int mmd_set_option(mmd_ctx* ctx, const char* key, long long value);
 
 #ifdef __cplusplus

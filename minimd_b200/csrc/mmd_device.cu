@@ -494,8 +494,13 @@ template <class T> struct Impl {
     CU(cudaMemcpyAsync(c->h_scal + 10, c->d_scal + 10, 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->max_bin_seen = std::max(c->max_bin_seen, c->h_scal[2]);
-    if (c->h_scal[0] & 1) return set_err(MMD_ERR_STATE, "atom outside the bin grid (lost atom / bad coordinates)");
-    if (c->h_scal[0] & 4) return set_err(MMD_ERR_STATE, "forward halo: a neighbor rank's message did not arrive (peer-memory path timed out)");
+    if (c->h_scal[0] & 5) {
+      // report once: the bits describe the state that was just examined, not whatever the caller uploads next
+      const int st = c->h_scal[0];
+      CU(cudaMemsetAsync(c->d_scal + 0, 0, sizeof(int), c->stream));
+      if (st & 1) return set_err(MMD_ERR_STATE, "atom outside the bin grid (lost atom / bad coordinates)");
+      return set_err(MMD_ERR_STATE, "forward halo: a neighbor rank's message did not arrive (peer-memory path timed out)");
+    }
     return MMD_OK;
   }
 
@@ -1349,6 +1354,9 @@ template <class T> struct Impl {
     {
       bool all_self = c->fuse_halo && c->nghost > 0;
       for (int ws = 0; ws < c->swaps.nswap; ws++) all_self = all_self && is_self(c, ws);
+      // one layer of swaps per dimension only: a second layer (box edge < cutneigh) composes shifts of +-2, which the
+      // packed 2-bit fields cannot hold and which x + 2*prd would not reproduce bit for bit
+      for (int d = 0; d < 3; d++) all_self = all_self && c->swaps.need[d] <= 1;
       if (all_self) {
         MM(c->ghost_src.reserve((size_t)c->nghost * sizeof(int), c->stream, 0, 1.3));
         MM(c->ghost_shift.reserve((size_t)c->nghost * sizeof(int), c->stream, 0, 1.3));

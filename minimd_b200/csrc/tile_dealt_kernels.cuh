@@ -64,18 +64,21 @@ tile_rows_deal_kernel(const unsigned short* __restrict__ rows, const int2* __res
     if (ta.x >= 0 && ta.x < nlocal) n = min(min(max(ta.y, 0), tcap), tcapq);
   }
   s_n[threadIdx.x] = n;
-  // sentinel pattern of a dealt row: word k holds slots 2k, 2k+1 of lane (2k >> 2) & 7
-  for (int k = threadIdx.x; k < DEAL_THREADS * dstride; k += DEAL_THREADS) {
-    const int wd = k % dstride;
-    const unsigned sv = (unsigned)(sentinel0 + ((wd >> 1) & 7));
-    s_dst[k] = sv | (sv << 16);
+  // sentinel pattern of a dealt row (every thread fills its own row: odd word stride, conflict-free):
+  // word k holds slots 2k, 2k+1, both of lane (k >> 1) & 7
+  {
+    unsigned* d = s_dst + threadIdx.x * dstride;
+    for (int k = 0; k < tcapq / 2; k++) {
+      const unsigned sv = (unsigned)(sentinel0 + ((k >> 1) & 7));
+      d[k] = sv | (sv << 16);
+    }
   }
   __syncthreads();
-  {  // coalesced copy-in: 16 bytes per thread and step
-    const int cpr = tcap / 8;
-    for (int idx = threadIdx.x; idx < DEAL_THREADS * cpr; idx += DEAL_THREADS) {
-      const int r = idx / cpr, ch = idx - r * cpr;
-      if (ch * 8 < s_n[r]) {
+  {  // coalesced copy-in: one row per warp and step, 16 bytes per lane
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int r = w; r < DEAL_THREADS; r += DEAL_THREADS / 32) {
+      const int nr = s_n[r];
+      for (int ch = lane; ch * 8 < nr; ch += 32) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(rows + (size_t)(q0 + r) * tcap + ch * 8));
         unsigned* d = s_src + r * sstride + ch * 4;
         d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
@@ -85,29 +88,19 @@ tile_rows_deal_kernel(const unsigned short* __restrict__ rows, const int2* __res
   __syncthreads();
   if (n > 0) {
     const unsigned short* __restrict__ src = reinterpret_cast<const unsigned short*>(s_src + threadIdx.x * sstride);
-    // class counts, 8 bits each (n <= 255): classes 0-3 in c0, 4-7 in c1
-    unsigned c0 = 0u, c1 = 0u;
-    for (int k = 0; k < n; k++) {
-      const unsigned ent = src[k];
-      const unsigned inc = 1u << ((ent & 3u) * 8u);
-      c0 += (ent & 4u) ? 0u : inc;
-      c1 += (ent & 4u) ? inc : 0u;
-    }
+    // class counts, 8 bits each (n <= 255)
+    unsigned long long cnt = 0ull;
+    for (int k = 0; k < n; k++) cnt += 1ull << ((src[k] & 7u) * 8u);
     // exclusive prefix over the classes (byte k of the product = sum of the bytes below k; totals < 256)
-    const unsigned tot0 = (c0 * 0x01010101u) >> 24;
-    unsigned p0 = c0 * 0x01010100u;
-    unsigned p1 = c1 * 0x01010100u + tot0 * 0x01010101u;
+    unsigned long long pre = cnt * 0x0101010101010100ull;
     const int G = (n + QL - 1) / QL;
     const float rG = 1.0f / (float)G;
     unsigned short* dst = reinterpret_cast<unsigned short*>(s_dst + threadIdx.x * dstride);
     for (int k = 0; k < n; k++) {
       const unsigned ent = src[k];
-      const unsigned sh = (ent & 3u) * 8u;
-      const bool hi = (ent & 4u) != 0u;
-      const int t = (int)(((hi ? p1 : p0) >> sh) & 0xffu);
-      const unsigned inc = 1u << sh;
-      p0 += hi ? 0u : inc;
-      p1 += hi ? inc : 0u;
+      const unsigned sh = (ent & 7u) * 8u;
+      const int t = (int)((pre >> sh) & 0xffull);
+      pre += 1ull << sh;
       // t / G for t < 256: (t + 0.5) / G stays >= 0.5 / G away from every integer, far above the FP32 error
       const int p = __float2int_rd(((float)t + 0.5f) * rG);
       const int g = t - p * G;
@@ -115,16 +108,17 @@ tile_rows_deal_kernel(const unsigned short* __restrict__ rows, const int2* __res
     }
   }
   __syncthreads();
-  // write out: ceil(n/32) blocks of 64 bytes per row, 16 bytes per thread and step
-  const int cpr = tcapq / 8;  // 16-byte chunks per row
-  for (int idx = threadIdx.x; idx < DEAL_THREADS * cpr; idx += DEAL_THREADS) {
-    const int r = idx / cpr, ch = idx - r * cpr;
-    const int nr = s_n[r];
-    if (ch * 8 < ((nr + QBLK - 1) / QBLK) * QBLK) {
-      const unsigned* sp = s_dst + r * dstride + ch * 4;
-      uint4 o;
-      o.x = sp[0]; o.y = sp[1]; o.z = sp[2]; o.w = sp[3];
-      *reinterpret_cast<uint4*>(rowsq + (size_t)(q0 + r) * tcapq + ch * 8) = o;
+  // write out: ceil(n/32) blocks of 64 bytes per row; one row per warp and step, 16 bytes per lane
+  {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int r = w; r < DEAL_THREADS; r += DEAL_THREADS / 32) {
+      const int nb = ((s_n[r] + QBLK - 1) / QBLK) * QBLK;
+      for (int ch = lane; ch * 8 < nb; ch += 32) {
+        const unsigned* sp = s_dst + r * dstride + ch * 4;
+        uint4 o;
+        o.x = sp[0]; o.y = sp[1]; o.z = sp[2]; o.w = sp[3];
+        *reinterpret_cast<uint4*>(rowsq + (size_t)(q0 + r) * tcapq + ch * 8) = o;
+      }
     }
   }
 }
