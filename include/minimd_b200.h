@@ -62,6 +62,10 @@ int mmd_atom_set_box(mmd_ctx* ctx, const double prd[3], const double lo[3], cons
 /* Replace the local atoms: x,v are MMD_float[nlocal*pad], type int[nlocal] (Atom::x/v/type).
  * Ghosts are dropped (nghost=0) -- exactly the state after create_atoms (ref/setup.cpp:315). */
 int mmd_atom_upload(mmd_ctx* ctx, const void* x, const void* v, const int* type, int nlocal, int pad);
+/* Declare the last (uploaded - nlocal) atoms of the preceding mmd_atom_upload to be ghosts: the host keeps Comm::borders
+ * (the mpi-spec compute_lj seam, mpi-spec/force_lj_custom.cpp:17-30, hands over x of nlocal + nghost atoms).  Ghosts made
+ * this way have no send lists on the device (their swap counts are zero): a forward / reverse halo does not touch them. */
+int mmd_atom_split(mmd_ctx* ctx, int nlocal);
 /* Overwrite x and/or v of atoms [first, first+count) without touching counts/lists
  * (the per-step H2D of a host-resident Atom). NULL pointers are skipped. */
 int mmd_atom_update(mmd_ctx* ctx, const void* x, const void* v, int first, int count, int pad);

@@ -67,6 +67,7 @@ SIGNATURES = {
     "mmd_ctx_launches": (C.c_longlong, [_P]),
     "mmd_atom_set_box": (_I, [_P, _DP, _DP, _DP]),
     "mmd_atom_upload": (_I, [_P, _P, _P, _P, _I, _I]),
+    "mmd_atom_split": (_I, [_P, _I]),
     "mmd_atom_update": (_I, [_P, _P, _P, _I, _I, _I]),
     "mmd_atom_download": (_I, [_P, _P, _P, _P, _P, _I, _I, _I]),
     "mmd_atom_counts": (_I, [_P, _IP, _IP, _IP]),

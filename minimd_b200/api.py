@@ -83,6 +83,10 @@ class Context:
         t = None if type_ is None else np.ascontiguousarray(type_, dtype=np.int32)
         check(self.lib.mmd_atom_upload(self.h, _ptr(x), _ptr(v), _ptr(t), n, pad))
 
+    def split(self, nlocal: int):
+        """The last (uploaded - nlocal) atoms of the preceding upload are ghosts (host-side Comm::borders)."""
+        check(self.lib.mmd_atom_split(self.h, int(nlocal)))
+
     def update(self, x=None, v=None, first=0):
         x = None if x is None else self._real(x)
         v = None if v is None else self._real(v)

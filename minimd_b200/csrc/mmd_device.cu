@@ -22,7 +22,7 @@
 #include "tile_kernels.cuh"
 #include "tile_dealt_kernels.cuh"
 #include "tile_build_lane.cuh"
-#include "tile_eam_kernels.cuh"
+#include "tile_eam_dealt.cuh"
 
 #ifdef MMD_WITH_NCCL
 #include <nccl.h>
@@ -157,7 +157,7 @@ struct mmd_ctx {
 
   // tile-resident lists (tile_kernels.cuh): 16-bit tile-local rows + shared-memory force kernels
   bool tile_enable = true;  // option "tile_lists"
-  bool tile_eam = false;    // option "tile_eam": tile-resident lists for the EAM force too
+  bool tile_eam = true;     // option "tile_eam": EAM on tile-resident, bank-dealt lists (tile_eam_dealt.cuh); 0 = classic rows
   bool tile_ok = false;     // bin grid / stencil admit the tiling (decided by mmd_neigh_setup)
   bool tile_build2 = true;  // option "tile_build2": CTA-per-tile build from shared memory (0: warp-per-bin build)
   bool list_tile = false;   // format of the current list
@@ -194,6 +194,8 @@ struct mmd_ctx {
   int eam_nr = 0, eam_nrho = 0;
   int eam_tpa = 8;
   DevBuf rho, fp;
+  DevBuf eam_blob1, eam_blob2, fp_s;  // pair-split spline tables of the dealt kernels, slot-ordered fp mirror
+  int eam_nkp = 0;
 
   // Comm
   bool have_comm = false;
@@ -515,9 +517,10 @@ template <class T> struct Impl {
   }
 
   // ---- neighbor build ------------------------------------------------------------------
-  // EAM: the owner-computes passes (tile_eam_kernels.cuh) evaluate every pair twice and the pair math is table-bound --
-  // measured slower than the classic half-list path at -s 64 (1.38 vs 0.99 ms per step), so they are opt-in ("tile_eam")
-  static bool want_tile(mmd_ctx* c) { return c->tile_enable && c->tile_ok && (!c->have_eam || c->tile_eam); }
+  // EAM runs on tile lists only through the dealt kernels, which need uniform tables (tile_eam_dealt.cuh)
+  static bool want_tile(mmd_ctx* c) {
+    return c->tile_enable && c->tile_ok && (!c->have_eam || (c->tile_eam && c->tile_dealt && c->eam_uniform));
+  }
 
   // ---- slot-ordered mirror of the positions (xs_mirror.cuh) -----------------------------------
   static XsMirror<T> mirror(mmd_ctx* c, int which) {
@@ -742,7 +745,7 @@ template <class T> struct Impl {
     c->tile_builds++;
     // bank-dealt copy of the rows for the LJ force kernel (tile_dealt_kernels.cuh)
     c->list_dealt = false;
-    if (c->tile_dealt && !c->have_eam) {
+    if (c->tile_dealt) {
       const int nrows = std::max(nall, 1);
       c->tcapq = dealt_capacity(std::min(c->tile_max_full, c->tcap));
       const size_t dsm = deal_smem_bytes(c->tcap, c->tcapq);
@@ -987,6 +990,25 @@ template <class T> struct Impl {
     MM(repack(hf, nrho, nrho_tot, 0, 3, c->eam_frho_der));
     MM(c->eam_cut.reserve((size_t)nn * sizeof(T), c->stream));
     CU(cudaMemcpy(c->eam_cut.p, hc, (size_t)nn * sizeof(T), cudaMemcpyHostToDevice));
+    {  // pair-split tables of the dealt kernels (type pair 0; used when all pairs share it)
+      const int nk = nr + 1, nkp = (nk + 3) & ~3;
+      c->eam_nkp = nkp;
+      std::vector<T> b1((size_t)nkp * 4, (T)0), b2((size_t)nkp * 7, (T)0);
+      for (int m = 0; m < nk; m++) {
+        const T* r7 = hr + (size_t)m * 7;
+        const T* z7 = hz + (size_t)m * 7;
+        b1[(size_t)2 * m + 0] = r7[3]; b1[(size_t)2 * m + 1] = r7[4];                                  // rhoA
+        b1[(size_t)2 * nkp + 2 * m + 0] = r7[5]; b1[(size_t)2 * nkp + 2 * m + 1] = r7[6];              // rhoB
+        b2[(size_t)2 * m + 0] = r7[0]; b2[(size_t)2 * m + 1] = r7[1];                                  // rdA
+        b2[(size_t)2 * nkp + 2 * m + 0] = z7[3]; b2[(size_t)2 * nkp + 2 * m + 1] = z7[4];              // z2A
+        b2[(size_t)4 * nkp + 2 * m + 0] = z7[5]; b2[(size_t)4 * nkp + 2 * m + 1] = z7[6];              // z2B
+        b2[(size_t)6 * nkp + m] = r7[2];                                                               // rdB
+      }
+      MM(c->eam_blob1.reserve(b1.size() * sizeof(T), c->stream));
+      MM(c->eam_blob2.reserve(b2.size() * sizeof(T), c->stream));
+      CU(cudaMemcpy(c->eam_blob1.p, b1.data(), b1.size() * sizeof(T), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(c->eam_blob2.p, b2.data(), b2.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
     c->eam_cut0 = (double)hc[0];
     c->eam_rdr = rdr; c->eam_rdrho = rdrho; c->eam_nr = nr; c->eam_nrho = nrho;
     c->have_eam = true;
@@ -1025,24 +1047,71 @@ template <class T> struct Impl {
     if (c->eam_uniform) return ev ? eam_launch<TPA, 1, 1>(c, half) : eam_launch<TPA, 0, 1>(c, half);
     return ev ? eam_launch<TPA, 1, 0>(c, half) : eam_launch<TPA, 0, 0>(c, half);
   }
-  // tile-resident list: owner-computes shared-memory passes (tile_eam_kernels.cuh)
-  template <int EV, int UNI> static int eam_tile_launch(mmd_ctx* c, int half) {
+  // tile-resident, bank-dealt list: owner-computes shared-memory passes (tile_eam_dealt.cuh)
+  static EAMDealtTabs<T> eam_dealt_tabs(mmd_ctx* c) {
+    EAMDealtTabs<T> D;
+    D.blob1 = c->eam_blob1.as<unsigned char>();
+    D.blob2 = c->eam_blob2.as<unsigned char>();
+    D.nkp = c->eam_nkp;
+    return D;
+  }
+  static bool eam_dealt_fits(mmd_ctx* c) {
+    const int scap = (c->tile_max_rows + 7) & ~7;
+    const EAMDealtTabs<T> D = eam_dealt_tabs(c);
+    return c->list_tile && c->list_dealt && c->eam_uniform &&
+           eam_dealt_smem_bytes<T>(c->tgeo.hcap, scap, 2, D) <= (size_t)(227 * 1024 - 2048);
+  }
+  // VP == nullptr: forces to f[]; else the velocity-Verlet halves ride in the pair pass's epilogue
+  template <int EV> static int eam_dealt_launch(mmd_ctx* c, int half, const VerletParams<T>* VP) {
     const EAMTables<T> E = eam_tables(c);
+    const EAMDealtTabs<T> D = eam_dealt_tabs(c);
     const TileGeo& g = c->tgeo;
-    const size_t sm1 = eam_tile_smem_bytes<T>(g.hcap, 1), sm2 = eam_tile_smem_bytes<T>(g.hcap, 2);
-    if (sm2 > (size_t)(227 * 1024 - 2048)) return set_err(MMD_ERR_STATE, "force_eam: halo window too large for the tile kernels");
-    MM(smem_optin(c, eam_tile_kernel<T, 1, EV, UNI>));
-    MM(smem_optin(c, eam_tile_kernel<T, 2, EV, UNI>));
+    const int scap = (c->tile_max_rows + 7) & ~7;
+    const size_t sm1 = eam_dealt_smem_bytes<T>(g.hcap, scap, 1, D), sm2 = eam_dealt_smem_bytes<T>(g.hcap, scap, 2, D);
+    if (!c->xs_valid) MM(xs_fill(c));
+    MM(c->fp_s.reserve(((size_t)std::max(c->cap, c->nlocal + c->nghost) + 64) * sizeof(T), c->stream));
     // ghosts receive no force in this scheme; keep their f at zero so that a following reverse halo is a no-op
-    if (half && c->nghost > 0) CU(cudaMemsetAsync(c->f.as<V>() + c->nlocal, 0, (size_t)c->nghost * sizeof(V), c->stream));
-#define EAMT_ARGS                                                                                                     \
-  c->x.as<V>(), c->f.as<V>(), g, c->tile_runs.as<int2>(), c->tile_center.as<int4>(), c->tile_info.as<int2>(),         \
-      c->tile_slots.as<int>(), c->trows.as<unsigned short>(), c->tnum.as<int2>(), c->tcap, c->nlocal, E, c->fp.as<T>(), \
-      c->d_ev
-    LAUNCH_SMEM(c, (eam_tile_kernel<T, 1, EV, UNI>), g.ntiles, TILE_THREADS, sm1, EAMT_ARGS);
+    if (half && !VP && c->nghost > 0) CU(cudaMemsetAsync(c->f.as<V>() + c->nlocal, 0, (size_t)c->nghost * sizeof(V), c->stream));
+    VerletParams<T> none;
+    memset(&none, 0, sizeof none);
+    const XsMirror<T> in = mirror(c, c->xs_cur), out = mirror(c, c->xs_cur ^ 1);
+#define EAMD_ARGS(vp)                                                                                                    \
+  c->x.as<V>(), c->f.as<V>(), g, c->tile_runs.as<int2>(), c->tile_center.as<int4>(), c->tile_info.as<int2>(), in,         \
+      c->trowsq.as<unsigned long long>(), c->tnum.as<int2>(), c->tcapq, c->nlocal, scap, E, D, c->fp.as<T>(),             \
+      c->fp_s.as<T>(), vp, out, c->d_ev
+    // 512 threads when two CTAs fit an SM, else one CTA of 1024 (the same 32 warps per SM either way)
+    if (2 * (sm1 + 1024) <= (size_t)227 * 1024) {
+      MM(smem_optin(c, eam_dealt_kernel<T, 1, EV, 0, 512>));
+      LAUNCH_SMEM(c, (eam_dealt_kernel<T, 1, EV, 0, 512>), g.ntiles, 512, sm1, EAMD_ARGS(none));
+    } else {
+      MM(smem_optin(c, eam_dealt_kernel<T, 1, EV, 0, 1024>));
+      LAUNCH_SMEM(c, (eam_dealt_kernel<T, 1, EV, 0, 1024>), g.ntiles, 1024, sm1, EAMD_ARGS(none));
+    }
     MM(forward_scalar(c, c->fp.as<T>()));
-    LAUNCH_SMEM(c, (eam_tile_kernel<T, 2, EV, UNI>), g.ntiles, TILE_THREADS, sm2, EAMT_ARGS);
-#undef EAMT_ARGS
+    if (c->nghost > 0)
+      LAUNCH(c, fp_mirror_ghosts_kernel<T>, div_up(c->nghost, TPB), TPB, c->fp.as<T>(), c->nlocal, c->nghost,
+             c->slot_of.as<int>(), c->fp_s.as<T>());
+    if (VP) {
+      MM(smem_optin(c, eam_dealt_kernel<T, 2, EV, 1, 1024>));
+      LAUNCH_SMEM(c, (eam_dealt_kernel<T, 2, EV, 1, 1024>), g.ntiles, 1024, sm2, EAMD_ARGS(*VP));
+      c->xs_cur ^= 1;
+    } else {
+      MM(smem_optin(c, eam_dealt_kernel<T, 2, EV, 0, 1024>));
+      LAUNCH_SMEM(c, (eam_dealt_kernel<T, 2, EV, 0, 1024>), g.ntiles, 1024, sm2, EAMD_ARGS(none));
+    }
+#undef EAMD_ARGS
+    return MMD_OK;
+  }
+  // EAM force of step n + finalIntegrate(n) + initialIntegrate(n+1); the new positions land in x_alt, which becomes x
+  static int eam_dealt_verlet(mmd_ctx* c, int half, int ev, double dt, double dtforce, double mass) {
+    VerletParams<T> VP;
+    VP.v = c->v.as<V>(); VP.x_out = c->x_alt.as<V>();
+    VP.dt = (T)dt; VP.dtforce = (T)dtforce; VP.mass = (T)mass;
+    MM(c->rho.reserve((size_t)c->cap * sizeof(T), c->stream));
+    MM(c->fp.reserve((size_t)c->cap * sizeof(T), c->stream));
+    if (ev) CU(cudaMemsetAsync(c->d_ev, 0, 4 * sizeof(double), c->stream));
+    MM(ev ? eam_dealt_launch<1>(c, half, &VP) : eam_dealt_launch<0>(c, half, &VP));
+    std::swap(c->x, c->x_alt);
     return MMD_OK;
   }
 
@@ -1054,11 +1123,8 @@ template <class T> struct Impl {
     if (ev) CU(cudaMemsetAsync(c->d_ev, 0, 4 * sizeof(double), c->stream));
     if (c->list_tile) {
       if ((half != 0) != (c->list_half != 0)) return set_err(MMD_ERR_STATE, "force_eam: list was built for the other neighbor style");
-      if (eam_tile_smem_bytes<T>(c->tgeo.hcap, 2) <= (size_t)(227 * 1024 - 2048)) {
-        if (c->eam_uniform) return ev ? eam_tile_launch<1, 1>(c, half) : eam_tile_launch<0, 1>(c, half);
-        return ev ? eam_tile_launch<1, 0>(c, half) : eam_tile_launch<0, 0>(c, half);
-      }
-      MM(ensure_classic(c));  // window too large for the pair pass: export once, continue on classic rows
+      if (eam_dealt_fits(c)) return ev ? eam_dealt_launch<1>(c, half, nullptr) : eam_dealt_launch<0>(c, half, nullptr);
+      MM(ensure_classic(c));  // window too large for the pair pass / per-type tables: export once, continue on classic rows
     }
     switch (c->eam_tpa) {
       case 1: return eam_dispatch<1>(c, half, ev);
@@ -1411,10 +1477,12 @@ template <class T> struct Impl {
       const int ev = p->thermo_nstat > 0 ? ((n + 1) % p->thermo_nstat == 0) : 0;
       // tile-resident lists: every atom's force is complete after the kernel -- nothing to clear, nothing to send back,
       // and the two velocity-Verlet halves that follow ride in the kernel's epilogue
-      const bool verlet_fused = c->fuse_force && c->fuse_integrate && c->list_tile && p->force_style == 0 && n < last;
+      const bool verlet_fused = c->fuse_force && c->fuse_integrate && c->list_tile && n < last &&
+                                (p->force_style == 0 || eam_dealt_fits(c));
       if (verlet_fused) {
         if (c->neigh_rows != c->nlocal) return set_err(MMD_ERR_STATE, "run: neighbor list is stale (build first)");
-        MM(lj_tile_verlet(c, p->halfneigh, ev, p->dt, p->dtforce, p->mass));
+        if (p->force_style == 0) MM(lj_tile_verlet(c, p->halfneigh, ev, p->dt, p->dtforce, p->mass));
+        else MM(eam_dealt_verlet(c, p->halfneigh, ev, p->dt, p->dtforce, p->mass));
       } else if (p->force_style == 0) MM(lj_async(c, p->halfneigh, p->ghost_newton, ev, !c->list_tile));
       else MM(eam_async(c, p->halfneigh, ev));
       MM(phase_mark(c, MMD_PHASE_FORCE));
@@ -1668,7 +1736,7 @@ int mmd_ctx_destroy(mmd_ctx* c) {
                     &c->eam_rho_der, &c->eam_z2_val, &c->eam_z2_der, &c->eam_frho_val, &c->eam_frho_der, &c->eam_cut,
                     &c->rho, &c->fp, &c->border_tiles, &c->sendbuf, &c->recvbuf, &c->exch_flag, &c->exch_pos,
                     &c->exch_holes, &c->ghost_src, &c->ghost_shift, &c->sruns, &c->tile_runs, &c->tile_center, &c->tile_info, &c->tile_slots, &c->tile_oslot, &c->trows,
-                    &c->tnum, &c->trowsq, &c->xs_rec[0], &c->xs_rec[1], &c->xs_z[0], &c->xs_z[1], &c->slot_of, &c->xs_types};
+                    &c->tnum, &c->trowsq, &c->xs_rec[0], &c->xs_rec[1], &c->xs_z[0], &c->xs_z[1], &c->slot_of, &c->xs_types, &c->eam_blob1, &c->eam_blob2, &c->fp_s};
   for (DevBuf* b : bufs) b->release();
   for (int w = 0; w < MMD_MAX_SWAPS; w++) c->sw[w].list.release();
   for (int r = 0; r < (int)c->peer_win.size(); r++)
@@ -1709,6 +1777,13 @@ int mmd_atom_upload(mmd_ctx* c, const void* x, const void* v, const int* type, i
   CHECK_CTX(c);
   if (!x || !v || nlocal < 0 || (pad != 3 && pad != 4)) return set_err(MMD_ERR_ARG, "atom_upload: bad arguments");
   return DISPATCH(c, Impl<double>::upload(c, x, v, type, nlocal, pad), Impl<float>::upload(c, x, v, type, nlocal, pad));
+}
+int mmd_atom_split(mmd_ctx* c, int nlocal) {
+  CHECK_CTX(c);
+  if (nlocal < 0 || nlocal > c->nlocal || c->nghost != 0) return set_err(MMD_ERR_ARG, "atom_split: call right after mmd_atom_upload with nlocal <= uploaded atoms");
+  c->nghost = c->nlocal - nlocal;
+  c->nlocal = nlocal;
+  return MMD_OK;
 }
 int mmd_atom_update(mmd_ctx* c, const void* x, const void* v, int first, int count, int pad) {
   CHECK_CTX(c);

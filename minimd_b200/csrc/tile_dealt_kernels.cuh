@@ -74,11 +74,12 @@ tile_rows_deal_kernel(const unsigned short* __restrict__ rows, const int2* __res
     }
   }
   __syncthreads();
-  {  // coalesced copy-in: one row per warp and step, 16 bytes per lane
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int r = w; r < DEAL_THREADS; r += DEAL_THREADS / 32) {
+  {  // coalesced copy-in: 8 rows per step, 16 lanes x 16 bytes per row (independent steps: the loads pipeline)
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll 4
+    for (int r = ty; r < DEAL_THREADS; r += DEAL_THREADS / 16) {
       const int nr = s_n[r];
-      for (int ch = lane; ch * 8 < nr; ch += 32) {
+      for (int ch = tx; ch * 8 < nr; ch += 16) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(rows + (size_t)(q0 + r) * tcap + ch * 8));
         unsigned* d = s_src + r * sstride + ch * 4;
         d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
@@ -108,12 +109,13 @@ tile_rows_deal_kernel(const unsigned short* __restrict__ rows, const int2* __res
     }
   }
   __syncthreads();
-  // write out: ceil(n/32) blocks of 64 bytes per row; one row per warp and step, 16 bytes per lane
+  // write out: ceil(n/32) blocks of 64 bytes per row; 8 rows per step, 16 lanes x 16 bytes per row
   {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int r = w; r < DEAL_THREADS; r += DEAL_THREADS / 32) {
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll 4
+    for (int r = ty; r < DEAL_THREADS; r += DEAL_THREADS / 16) {
       const int nb = ((s_n[r] + QBLK - 1) / QBLK) * QBLK;
-      for (int ch = lane; ch * 8 < nb; ch += 32) {
+      for (int ch = tx; ch * 8 < nb; ch += 16) {
         const unsigned* sp = s_dst + r * dstride + ch * 4;
         uint4 o;
         o.x = sp[0]; o.y = sp[1]; o.z = sp[2]; o.w = sp[3];

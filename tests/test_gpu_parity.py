@@ -224,6 +224,40 @@ def test_lj_force_energy_virial(half, gn, tpa, prec):
     assert_close(f0, f, 1e-13 if prec == "f64" else 1e-5, "f(ev=0) vs f(ev=1)")
 
 
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("half,gn", [(1, 1), (1, 0), (0, 0)])
+def test_lj_compute_seam_with_host_lists(half, gn, prec):
+    """The mpi-spec compute_lj seam (mpi-spec/force_lj_custom.cpp:17-30): the HOST owns ghosts and neighbor lists and
+    hands over x of nlocal + nghost atoms and its rows on every call -- mmd_atom_upload + mmd_atom_split +
+    mmd_neigh_upload + mmd_force_lj_compute; forces (ghost contributions of half lists included) come back."""
+    o = melted(dict(nx=7, ny=6, nz=8, halfneigh=half, ghost_newton=gn), 40, prec)
+    c = context_from_oracle(o, upload_atoms=False)
+    nl, na = o.nlocal, o.nall
+    v = np.zeros((na, 3), dtype=c.real)
+    v[:nl] = o.v(nl)
+    c.upload(o.x(na), v, o.type(na))
+    c.split(nl)
+    assert c.counts()[:2] == (nl, na - nl)
+    num, nb = o.numneigh(), o.neighbors()
+    c.neigh_upload(num, nb)
+    assert c.query("list_tile") == 0
+    o.seti("evflag", 1)
+    o.call("force_compute")
+    eng, vir = c.lj_compute(half, gn, 1)
+    n = na if half else nl
+    assert_close(c.download("f", count=n)["f"], o.f(n), ktol(prec), "f")
+    etol = 1e-11 if prec == "f64" else 2e-3
+    assert abs(eng - o.getr("eng_vdwl")) <= etol * abs(o.getr("eng_vdwl"))
+    # positions change, lists stay: the per-step path of the seam
+    o.call("initial_integrate")
+    o.call("communicate")
+    c.update(x=o.x(na))
+    o.seti("evflag", 0)
+    o.call("force_compute")
+    c.lj_compute(half, gn, 0)
+    assert_close(c.download("f", count=n)["f"], o.f(n), ktol(prec), "f after update")
+
+
 @pytest.mark.parametrize("tile", [1, 0])
 def test_lj_per_type_tables_path(tile):
     """Distinct epsilon/sigma per type pair exercises the non-uniform table kernels."""
