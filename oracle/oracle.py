@@ -35,6 +35,14 @@ def build(force: bool = False) -> None:
                               stdout=subprocess.DEVNULL)
     if os.path.isdir(os.environ.get("MINIMD_REFERENCE", "/root/reference")):
         subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")], stdout=subprocess.DEVNULL)
+        # the drop-in proof: the reference program with one translation unit replaced by a C-ABI caller (tests/dropin/);
+        # rebuilt when the library or the replacement units are newer than the binaries
+        lib = os.path.join(os.path.dirname(HERE), "minimd_b200", "lib", "libminimd_b200.so")
+        outs = [os.path.join(REF_DIR, n) for n in ("miniMD_dropin_run_f64", "miniMD_dropin_force_f64")]
+        srcs = [lib] + [os.path.join(os.path.dirname(HERE), "tests", "dropin", f) for f in ("integrate_b200.cpp", "force_lj_b200.cpp")]
+        if os.path.exists(lib) and (force or not all(os.path.exists(o) for o in outs) or
+                                    max(os.path.getmtime(s_) for s_ in srcs[1:]) > min(os.path.getmtime(o) for o in outs)):
+            subprocess.check_call(["bash", os.path.join(HERE, "build_dropin.sh")], stdout=subprocess.DEVNULL)
 
 
 class OrcConfig(C.Structure):
