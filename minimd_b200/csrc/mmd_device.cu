@@ -76,6 +76,16 @@ static inline int launch_smem_impl(int line, C* ctx, K kern, int grid, int block
   return MMD_OK;
 }
 #define LAUNCH_SMEM(ctx, kern, grid, block, smem, ...) MM(launch_smem_impl(__LINE__, ctx, kern, grid, block, smem, __VA_ARGS__))
+template <class C, class K, class... Args>
+static inline int launch_on_impl(int line, C* ctx, cudaStream_t st, K kern, int grid, int block, size_t smem, Args... args) {
+  if (grid <= 0) return MMD_OK;
+  kern<<<grid, block, smem, st>>>(args...);
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return launch_fail(line, e);
+  return MMD_OK;
+}
+#define LAUNCH_ON(ctx, st, kern, grid, block, smem, ...) MM(launch_on_impl(__LINE__, ctx, st, kern, grid, block, smem, __VA_ARGS__))
 
 #ifdef MMD_WITH_NCCL
 #define NC(call)                                                                                  \
@@ -181,6 +191,16 @@ struct mmd_ctx {
   DevBuf xs_rec[2], xs_z[2], slot_of, xs_types;
   int xs_cur = 0;
   bool xs_valid = false;    // the current mirror buffer agrees with x[] for every binned atom
+  // several ranks: interior tiles (no ghost in the halo window) run on a second stream while the forward halo is in flight
+  bool split_enable = true;   // option "split_force"
+  bool split_ready = false;   // tile_split holds the lists of the current neighbor list
+  bool split_active = false;  // work may be pending on stream2 (joined before anything else touches the atoms)
+  bool ev_int_valid = false;
+  DevBuf tile_split;          // [2 * ntiles] interior tiles, then boundary tiles
+  int n_interior = 0, n_boundary = 0;
+  long long split_steps = 0;
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_int = nullptr, ev_bnd = nullptr;
   std::set<const void*> smem_optin;  // kernels of this context's device already opted in to > 48 KB dynamic shared memory
 
   // Force
@@ -224,7 +244,7 @@ struct mmd_ctx {
   // device scalars + pinned mirror
   // d_scal ints : [0] status, [1] max_n, [2] max_bin, [3] border total 0, [4] border total 1, [5] scan total,
   //               [6..9] exchange/border counts, [10] max full row, [11] max halo window, [12] tile status,
-  //               [13] tile row counter, [14] max rows of a tile
+  //               [13] tile row counter, [14] max rows of a tile, [16] interior tiles, [17] boundary tiles
   // d_ev doubles: [0] eng, [1] virial, [2] sum m v^2, [3] embed energy
   int* d_scal = nullptr;
   unsigned long long* d_total = nullptr;
@@ -757,6 +777,18 @@ template <class T> struct Impl {
         c->list_dealt = true;
         c->xs_valid = false;
         MM(xs_fill(c));
+        c->split_ready = false;
+        if (c->nranks > 1 && c->split_enable && c->stream2) {
+          MM(c->tile_split.reserve((size_t)2 * g.ntiles * sizeof(int), c->stream));
+          CU(cudaMemsetAsync(c->d_scal + 16, 0, 2 * sizeof(int), c->stream));
+          LAUNCH(c, tile_classify_kernel, div_up(g.ntiles, 4), 128, g, c->tile_runs.as<int2>(), c->tile_info.as<int2>(),
+                 c->tile_slots.as<int>(), c->nlocal, c->tile_split.as<int>(), c->d_scal + 16);
+          CU(cudaMemcpyAsync(c->h_scal + 16, c->d_scal + 16, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+          CU(cudaStreamSynchronize(c->stream));
+          c->n_interior = c->h_scal[16];
+          c->n_boundary = c->h_scal[17];
+          c->split_ready = true;
+        }
       }
     }
     *done = true;
@@ -865,7 +897,9 @@ template <class T> struct Impl {
     return ev ? lj_launch<TPA, 0, 0, 1>(c) : lj_launch<TPA, 0, 0, 0>(c);
   }
   // tile-resident list: owner-computes shared-memory kernel (tile_kernels.cuh)
-  template <int EV, int UNI, int INTEG> static int lj_tile_launch(mmd_ctx* c, int half, const VerletParams<T>& VP) {
+  // part: 0 = every tile on the context's stream; 1 = interior tiles on stream2; 2 = boundary tiles on the context's
+  // stream (dealt lists of several ranks only, see run())
+  template <int EV, int UNI, int INTEG> static int lj_tile_launch(mmd_ctx* c, int half, const VerletParams<T>& VP, int part = 0) {
     LJTileParams<T> P;
     P.cutforcesq = (T)c->lj_cut0; P.sigma6 = (T)c->lj_s60; P.epsilon = (T)c->lj_eps0;
     P.cutforcesq_tab = c->lj_cut.as<T>(); P.sigma6_tab = c->lj_s6.as<T>(); P.epsilon_tab = c->lj_eps.as<T>();
@@ -884,12 +918,16 @@ template <class T> struct Impl {
       Q.cutforcesq_tab = P.cutforcesq_tab; Q.sigma6_tab = P.sigma6_tab; Q.epsilon_tab = P.epsilon_tab;
       Q.ntypes = P.ntypes; Q.e_scale = P.e_scale; Q.v_scale = P.v_scale;
       MM(smem_optin(c, force_lj_dealt_kernel<T, EV, UNI, INTEG>));
-      LAUNCH_SMEM(c, (force_lj_dealt_kernel<T, EV, UNI, INTEG>), g.ntiles, TILE_THREADS, qwin_smem_bytes<T>(g.hcap, !UNI, scap),
-                  c->x.as<V>(), c->f.as<V>(), g, c->tile_runs.as<int2>(), c->tile_center.as<int4>(), c->tile_info.as<int2>(),
-                  mirror(c, c->xs_cur), c->xs_types.as<unsigned char>(), c->trowsq.as<unsigned long long>(), c->tnum.as<int2>(),
-                  c->tcapq, c->nlocal, scap, Q, VP, mirror(c, c->xs_cur ^ 1), c->d_ev);
-      if (INTEG) c->xs_cur ^= 1;  // the epilogue wrote the local atoms' new positions into the other buffer (ghosts follow
-                                  // with the next forward halo, as in x_alt)
+      const int* list = part == 0 ? (const int*)nullptr : c->tile_split.as<int>() + (part == 2 ? g.ntiles : 0);
+      const int grid = part == 0 ? g.ntiles : (part == 1 ? c->n_interior : c->n_boundary);
+      LAUNCH_ON(c, part == 1 ? c->stream2 : c->stream, (force_lj_dealt_kernel<T, EV, UNI, INTEG>), grid, TILE_THREADS,
+                qwin_smem_bytes<T>(g.hcap, !UNI, scap), c->x.as<V>(), c->f.as<V>(), g, c->tile_runs.as<int2>(),
+                c->tile_center.as<int4>(), c->tile_info.as<int2>(), mirror(c, c->xs_cur), c->xs_types.as<unsigned char>(),
+                c->trowsq.as<unsigned long long>(), c->tnum.as<int2>(), c->tcapq, c->nlocal, scap, Q, VP,
+                mirror(c, c->xs_cur ^ 1), c->d_ev, list);
+      // the epilogue wrote the local atoms' new positions into the other mirror buffer (ghosts follow with the next
+      // forward halo, as in x_alt); with a split launch the buffers flip once, after the second part
+      if (INTEG && part != 1) c->xs_cur ^= 1;
       return MMD_OK;
     }
     const size_t smem = tile_smem_bytes<T>(g.hcap, !UNI);
@@ -909,6 +947,48 @@ template <class T> struct Impl {
     if (c->lj_uniform) MM(ev ? (lj_tile_launch<1, 1, 1>(c, half, VP)) : (lj_tile_launch<0, 1, 1>(c, half, VP)));
     else MM(ev ? (lj_tile_launch<1, 0, 1>(c, half, VP)) : (lj_tile_launch<0, 0, 1>(c, half, VP)));
     std::swap(c->x, c->x_alt);
+    return MMD_OK;
+  }
+  static bool split_usable(mmd_ctx* c) {
+    return c->split_enable && c->nranks > 1 && c->split_ready && c->list_tile && c->list_dealt && c->n_interior > 0 &&
+           c->stream2 != nullptr;
+  }
+  // anything that is not a split step waits for the interior kernels still running on stream2
+  static int split_join(mmd_ctx* c) {
+    if (c->split_active) {
+      if (c->ev_int_valid) CU(cudaStreamWaitEvent(c->stream, c->ev_int, 0));
+      c->split_active = false;
+      c->ev_int_valid = false;
+    }
+    return MMD_OK;
+  }
+  // One fused step of several ranks with the forward halo hidden behind the interior tiles:
+  //   stream2: [boundary(n-1) done]                    interior(n)
+  //   stream : [interior(n-1) done]  forward halo(n)   boundary(n)
+  // Both parts read the position buffers of step n and write those of step n+1; the halo writes ghost slots only, which
+  // no interior window contains.  (No energies on this path: thermo steps run the single launch.)
+  static int lj_split_step(mmd_ctx* c, int half, double dt, double dtforce, double mass) {
+    VerletParams<T> VP;
+    VP.v = c->v.as<V>(); VP.x_out = c->x_alt.as<V>();
+    VP.dt = (T)dt; VP.dtforce = (T)dtforce; VP.mass = (T)mass;
+    if (!c->xs_valid) MM(xs_fill(c));
+    if (!c->split_active) {  // first split step after other work: stream2 starts behind everything queued so far
+      CU(cudaEventRecord(c->ev_bnd, c->stream));
+      c->split_active = true;
+      c->ev_int_valid = false;
+    }
+    CU(cudaStreamWaitEvent(c->stream2, c->ev_bnd, 0));
+    if (c->lj_uniform) MM((lj_tile_launch<0, 1, 1>(c, half, VP, 1))); else MM((lj_tile_launch<0, 0, 1>(c, half, VP, 1)));
+    const bool had_int = c->ev_int_valid;
+    if (had_int) CU(cudaStreamWaitEvent(c->stream, c->ev_int, 0));
+    CU(cudaEventRecord(c->ev_int, c->stream2));
+    c->ev_int_valid = true;
+    MM(communicate(c, false));
+    MM(phase_mark(c, MMD_PHASE_COMM));
+    if (c->lj_uniform) MM((lj_tile_launch<0, 1, 1>(c, half, VP, 2))); else MM((lj_tile_launch<0, 0, 1>(c, half, VP, 2)));
+    CU(cudaEventRecord(c->ev_bnd, c->stream));
+    std::swap(c->x, c->x_alt);
+    c->split_steps++;
     return MMD_OK;
   }
 
@@ -1459,6 +1539,16 @@ template <class T> struct Impl {
         MM(initial(c, p->dt, p->dtforce, false));
         MM(phase_mark(c, MMD_PHASE_INTEGRATE));
       }
+      const int ev = p->thermo_nstat > 0 ? ((n + 1) % p->thermo_nstat == 0) : 0;
+      // several ranks, dealt LJ lists, no energies wanted: the forward halo of this step runs behind the interior tiles
+      const bool do_split = ((n + 1) % p->neigh_every) != 0 && n != p->first_step && n < last && !ev && p->force_style == 0 &&
+                            c->fuse_force && c->fuse_integrate && c->neigh_rows == c->nlocal && split_usable(c);
+      if (do_split) {
+        MM(lj_split_step(c, p->halfneigh, p->dt, p->dtforce, p->mass));
+        MM(phase_mark(c, MMD_PHASE_FORCE));
+        continue;
+      }
+      MM(split_join(c));
       if ((n + 1) % p->neigh_every) {
         MM(communicate(c, false));
         MM(phase_mark(c, MMD_PHASE_COMM));
@@ -1474,7 +1564,6 @@ template <class T> struct Impl {
         MM(build(c, p->halfneigh, p->ghost_newton, &mx, nullptr));
         MM(phase_mark(c, MMD_PHASE_NEIGH));
       }
-      const int ev = p->thermo_nstat > 0 ? ((n + 1) % p->thermo_nstat == 0) : 0;
       // tile-resident lists: every atom's force is complete after the kernel -- nothing to clear, nothing to send back,
       // and the two velocity-Verlet halves that follow ride in the kernel's epilogue
       const bool verlet_fused = c->fuse_force && c->fuse_integrate && c->list_tile && n < last &&
@@ -1505,6 +1594,7 @@ template <class T> struct Impl {
         ns++;
       }
     }
+    MM(split_join(c));
     if (elapsed_ms) {
       CU(cudaEventRecord(c->ev1, c->stream));
       CU(cudaEventSynchronize(c->ev1));
@@ -1706,19 +1796,23 @@ int mmd_ctx_create(int device, int precision_bytes, int ntypes, void* stream, mm
   if (stream) {
     c->stream = (cudaStream_t)stream;
   } else {
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // highest priority: with several ranks the halo and boundary kernels launched here must get SM slots ahead of the
+    // interior kernels queued on the low-priority second stream (CTA-granular scheduling, nothing is preempted)
+    int pr_least = 0, pr_greatest = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+    CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, pr_greatest));
     c->own_stream = true;
   }
-  CU(cudaMalloc(&c->d_scal, 16 * sizeof(int)));
+  CU(cudaMalloc(&c->d_scal, 32 * sizeof(int)));
   CU(cudaMalloc(&c->d_total, sizeof(unsigned long long)));
   CU(cudaMalloc(&c->d_ev, 32 * sizeof(double)));
-  CU(cudaMemset(c->d_scal, 0, 16 * sizeof(int)));
+  CU(cudaMemset(c->d_scal, 0, 32 * sizeof(int)));
   CU(cudaMemset(c->d_total, 0, sizeof(unsigned long long)));
   CU(cudaMemset(c->d_ev, 0, 32 * sizeof(double)));
-  CU(cudaMallocHost(&c->h_scal, 16 * sizeof(int)));
+  CU(cudaMallocHost(&c->h_scal, 32 * sizeof(int)));
   CU(cudaMallocHost(&c->h_total, sizeof(unsigned long long)));
   CU(cudaMallocHost(&c->h_ev, 4 * sizeof(double)));
-  memset(c->h_scal, 0, 16 * sizeof(int));
+  memset(c->h_scal, 0, 32 * sizeof(int));
   CU(cudaEventCreate(&c->ev0));
   CU(cudaEventCreate(&c->ev1));
   memset(&c->swaps, 0, sizeof c->swaps);
@@ -1736,7 +1830,7 @@ int mmd_ctx_destroy(mmd_ctx* c) {
                     &c->eam_rho_der, &c->eam_z2_val, &c->eam_z2_der, &c->eam_frho_val, &c->eam_frho_der, &c->eam_cut,
                     &c->rho, &c->fp, &c->border_tiles, &c->sendbuf, &c->recvbuf, &c->exch_flag, &c->exch_pos,
                     &c->exch_holes, &c->ghost_src, &c->ghost_shift, &c->sruns, &c->tile_runs, &c->tile_center, &c->tile_info, &c->tile_slots, &c->tile_oslot, &c->trows,
-                    &c->tnum, &c->trowsq, &c->xs_rec[0], &c->xs_rec[1], &c->xs_z[0], &c->xs_z[1], &c->slot_of, &c->xs_types, &c->eam_blob1, &c->eam_blob2, &c->fp_s};
+                    &c->tnum, &c->trowsq, &c->xs_rec[0], &c->xs_rec[1], &c->xs_z[0], &c->xs_z[1], &c->slot_of, &c->xs_types, &c->eam_blob1, &c->eam_blob2, &c->fp_s, &c->tile_split};
   for (DevBuf* b : bufs) b->release();
   for (int w = 0; w < MMD_MAX_SWAPS; w++) c->sw[w].list.release();
   for (int r = 0; r < (int)c->peer_win.size(); r++)
@@ -1749,6 +1843,9 @@ int mmd_ctx_destroy(mmd_ctx* c) {
   cudaFree(c->d_scal); cudaFree(c->d_total); cudaFree(c->d_ev);
   cudaFreeHost(c->h_scal); cudaFreeHost(c->h_total); cudaFreeHost(c->h_ev);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+  if (c->ev_int) cudaEventDestroy(c->ev_int);
+  if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
   for (cudaEvent_t e : c->marks) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -2090,6 +2187,13 @@ int mmd_comm_nccl_init(mmd_ctx* c, const void* id128, int rank, int nranks) {
   NC(ncclCommInitRank(&c->nccl, nranks, id, rank));
   c->rank = rank;
   c->nranks = nranks;
+  if (nranks > 1 && !c->stream2) {
+    int pr_least = 0, pr_greatest = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+    CU(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, pr_least));
+    CU(cudaEventCreateWithFlags(&c->ev_int, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming));
+  }
   if (nranks > 1 && c->p2p_enable) MM(p2p_setup(c));
   return MMD_OK;
 #else
@@ -2203,6 +2307,9 @@ int mmd_query_int(mmd_ctx* c, const char* key, long long* value) {
   else if (k == "list_tile") *value = c->list_tile;
   else if (k == "list_dealt") *value = c->list_tile && c->list_dealt;
   else if (k == "tile_dealt_capacity") *value = c->tcapq;
+  else if (k == "split_steps") *value = c->split_steps;
+  else if (k == "tile_interior") *value = c->split_ready ? c->n_interior : 0;
+  else if (k == "tile_boundary") *value = c->split_ready ? c->n_boundary : 0;
   else if (k == "tile_ok") *value = c->tile_ok;
   else if (k == "tile_builds") *value = c->tile_builds;
   else if (k == "tile_fallbacks") *value = c->tile_fallbacks;
@@ -2231,6 +2338,9 @@ int mmd_set_option(mmd_ctx* c, const char* key, long long value) {
     if (!c->fuse_halo) c->ghosts_resolved = false;
   } else if (k == "tile_dealt") {  // 1: the LJ force kernel walks bank-dealt rows (quarter warp per atom); 0: one lane pair per row
     c->tile_dealt = value != 0;     // takes effect at the next neighbor build
+  } else if (k == "split_force") {  // several ranks: interior tiles on a second stream behind the forward halo
+    c->split_enable = value != 0;
+    if (!c->split_enable) c->split_ready = false;
   } else if (k == "tile_lane_build") {
     c->tile_lane_build = value != 0;
   } else if (k == "tile_xsort") {

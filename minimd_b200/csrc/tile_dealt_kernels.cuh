@@ -305,9 +305,10 @@ force_lj_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Ti
                       const int4* __restrict__ tile_center, const int2* __restrict__ tile_info, XsMirror<T> xs_in,
                       const unsigned char* __restrict__ types_s, const unsigned long long* __restrict__ rowsq,
                       const int2* __restrict__ row_atom, int tcapq, int nlocal, int scap, LJDealtParams<T> P,
-                      VerletParams<T> VP, XsMirror<T> xs_out, double* __restrict__ ev_out) {
+                      VerletParams<T> VP, XsMirror<T> xs_out, double* __restrict__ ev_out,
+                      const int* __restrict__ tile_list /* nullptr: every tile, blockIdx.x = tile */) {
   extern __shared__ __align__(16) unsigned char tile_smem_raw[];
-  const int t = blockIdx.x;
+  const int t = tile_list ? __ldg(tile_list + blockIdx.x) : blockIdx.x;
   const int2 inf = tile_info[t];
   if (inf.y == 0) return;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
@@ -499,6 +500,35 @@ force_lj_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Ti
       const double v2[2] = {eng * P.e_scale, vir * P.v_scale};
       block_accumulate<2>(v2, ev_out);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Interior / boundary split for several ranks: a tile whose halo window holds no ghost atom needs nothing from the
+// forward halo, so its force can run while the halo of the same step is still in flight.  One warp per tile scans the
+// window's slots; lists[0 .. counts[0]) receives the interior tiles, lists[ntiles .. ntiles + counts[1]) the others.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+tile_classify_kernel(TileGeo g, const int2* __restrict__ tile_runs, const int2* __restrict__ tile_info,
+                     const int* __restrict__ slots, int nlocal, int* __restrict__ lists, int* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (t >= g.ntiles) return;
+  const int2 inf = tile_info[t];
+  if (inf.y == 0) return;
+  const int2* tr = tile_runs + (size_t)t * g.nrun;
+  // the window's runs are contiguous slot ranges; run p ends where run p+1 starts in tile-local numbering
+  bool ghost = false;
+  for (int p = 0; p < g.nrun && !ghost; p++) {
+    const int2 r = tr[p];
+    const int len = (p + 1 < g.nrun ? tr[p + 1].y : inf.x) - r.y;
+    bool gl = false;
+    for (int k = lane; k < len; k += 32) gl = gl || (__ldg(slots + r.x + k) >= nlocal);
+    ghost = __any_sync(0xffffffffu, gl);
+  }
+  if (lane == 0) {
+    const int k = atomicAdd(counts + (ghost ? 1 : 0), 1);
+    lists[(ghost ? g.ntiles : 0) + k] = t;
   }
 }
 

@@ -32,6 +32,8 @@ CASES = [
     (2, ["--cells", 10, 10, 20, "--force", "eam", "--half_neigh", 0]),
     (2, ["--cells", 10, 10, 20, "--force", "eam", "--half_neigh", 1]),
     (2, ["--cells", 12, 12, 24, "--p2p", 0]),
+    (2, ["--cells", 32, 32, 64]),                  # large enough for interior tiles: halo hidden behind the interior force
+    (2, ["--cells", 32, 32, 64, "--split", 0]),
     (4, ["--cells", 12, 24, 24]),
     (8, ["--cells", 24, 24, 24]),
     (8, ["--cells", 20, 20, 20, "--force", "eam", "--half_neigh", 0]),
@@ -47,3 +49,5 @@ def test_multi_gpu_matches_single_rank_oracle(n, extra):
     assert res["ranks"] == n and res["migrated_atoms"] > 0
     if "--p2p" in extra:
         assert res["p2p_active"] == 0 and res["p2p_calls"] == 0
+    if extra[:4] == ["--cells", 32, 32, 64]:
+        assert (res["split_steps"] > 0) == ("--split" not in extra), res

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--precision", default="f64")
     ap.add_argument("--tol", type=float, default=1e-9)
     ap.add_argument("--p2p", type=int, default=1, help="1: forward halo over peer-memory windows; 0: NCCL send/recv")
+    ap.add_argument("--split", type=int, default=1, help="1: interior tiles on a second stream behind the forward halo; 0: one force launch per step")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -52,6 +53,8 @@ def main():
         sim = Simulation(args, a.precision, rank=rank, nranks=world, device=local, nccl_id=idt.cpu().numpy().tobytes())
         if not a.p2p:
             sim.context().set_option("p2p_halo", 0)
+        if not a.split:
+            sim.context().set_option("split_force", 0)
         neigh0 = torch.tensor([sim.geti("total_neigh")], dtype=torch.float64, device="cuda")
         dist.all_reduce(neigh0)
         ms = sim.run()
@@ -61,6 +64,7 @@ def main():
         dist.all_reduce(cnt)
         grid = [sim.geti(f"procgrid{d}") for d in range(3)]
         p2p = [sim.context().query("p2p_active"), sim.context().query("p2p_calls")]
+        split = [sim.context().query("split_steps"), sim.context().query("tile_interior"), sim.context().query("tile_boundary")]
         sim.close()
     ok, res = True, None
     if rank == 0:
@@ -83,6 +87,7 @@ def main():
         res = {"ok": bool(ok), "ranks": world, "procgrid": grid, "cells": a.cells, "force": a.force, "errs": errs,
                "natoms": int(cnt[0].item()), "neigh_step0": [int(neigh0.item()), n0], "neigh_end": [int(cnt[1].item()), n1],
                "nghost_sum": int(cnt[2].item()), "migrated_atoms": int(cnt[3].item()), "device_ms": ms, "p2p_active": p2p[0], "p2p_calls": p2p[1],
+               "split_steps": split[0], "tiles_interior_boundary_rank0": split[1:],
                "last": [st[-1], T[-1], U[-1], P[-1]]}
         print(json.dumps(res), flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
