@@ -406,8 +406,16 @@ def measure_resident(a, D, sim, ctx, local_rank, with_clocks):
     per_gpu_rate = value * 1e6 / D.n
     step_roofline = {"bytes_per_atom_step": step_bytes, "achieved": per_gpu_rate * step_bytes / 1e9, "peak": peak,
                      "unit": "GB/s", "frac": per_gpu_rate * step_bytes / 1e9 / peak}
+    kp = None
+    if any(kv.startswith("kernel_profile=") and kv != "kernel_profile=0" for kv in a.opt):
+        n_cta = ctx.query("cta_count")
+        if n_cta > 0:   # clock64 sums per CTA of the LJ tile force kernel (diagnostic run: not a bench number)
+            kp = {"ctas": n_cta, "stage_clocks_per_cta": ctx.query("stage_clocks") / n_cta,
+                  "cta_clocks": ctx.query("cta_clocks") / n_cta,
+                  "staging_share_of_cta_lifetime": ctx.query("stage_clocks") / max(ctx.query("cta_clocks"), 1)}
     st, T, U, P = sim.thermo()
     return {
+        "kernel_profile": kp,
         "value": value, "ms_per_step": ms_total / a.steps, "md_steps_timed": md_steps, "device_ms_inside_mmd_run": inner_ms,
         "phase_ms_per_step": {k: v[0] / a.steps for k, v in phases.items()}, "roofline": roofline,
         "step_roofline": step_roofline, "gpu_launches": int(launches), "clocks": clk,
@@ -526,7 +534,7 @@ def own_arm(a, n_gpus, rank, local_rank):
         "dtype": a.precision, "data": "synthetic", "config": workload_config(a, n_gpus),
         "md_steps_timed": r["md_steps_timed"], "device_ms_inside_mmd_run": r["device_ms_inside_mmd_run"],
         "phase_ms_per_step": r["phase_ms_per_step"], "roofline": r["roofline"], "step_roofline": r["step_roofline"],
-        "e2e": e2e, "gpu_launches": r["gpu_launches"], "clocks": r["clocks"], "thermo_last": r["thermo_last"],
+        "kernel_profile": r["kernel_profile"], "e2e": e2e, "gpu_launches": r["gpu_launches"], "clocks": r["clocks"], "thermo_last": r["thermo_last"],
         "counts": r["counts"],
         "halo_transport": ("none (single rank: device-local self swaps)" if n_gpus == 1 else
                            ("peer-memory windows over NVLink (CUDA IPC), fused pack+remote store / wait+unpack kernels"

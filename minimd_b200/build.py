@@ -64,6 +64,8 @@ def build_device(force: bool = False, verbose: bool = False) -> str:
                "-o", out, os.path.join(CSRC, "mmd_device.cu"), *_nccl_flags()]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
+        if os.environ.get("MMD_KERNEL_PROFILE"):   # diagnostic build: clock64 sums in the LJ tile force kernels
+            cmd.insert(1, "-DMMD_KERNEL_PROFILE")
         _run(cmd)
     return out
 

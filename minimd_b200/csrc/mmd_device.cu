@@ -175,6 +175,7 @@ struct mmd_ctx {
   int nsruns = 0;           // runs of the symmetric (full) stencil
   DevBuf sruns, tile_runs, tile_center, tile_info, tile_slots, tile_oslot, trows, tnum;
   bool tile_xsort = true;     // option "tile_xsort": x-sorted windows + interval build
+  bool tile_pair_build = true;  // option "tile_pair_build": the interval build sweeps two atoms of a bin at a time
   bool tile_lane_build = false;  // option "tile_lane_build": interval build with one lane per atom (default 0: one warp per atom, measured faster)
   bool list_xsorted = false;  // the current list was built on x-sorted windows
   int tcap = 0;             // row capacity (16-bit entries, multiple of 8)
@@ -196,9 +197,13 @@ struct mmd_ctx {
   bool split_ready = false;   // tile_split holds the lists of the current neighbor list
   bool split_active = false;  // work may be pending on stream2 (joined before anything else touches the atoms)
   bool ev_int_valid = false;
-  DevBuf tile_split;          // [2 * ntiles] interior tiles, then boundary tiles
-  int n_interior = 0, n_boundary = 0;
+  DevBuf tile_split;          // [3 * ntiles] interior tiles | boundary tiles | all tiles that own local atoms
+  int n_interior = 0, n_boundary = 0, n_active = 0;
   long long split_steps = 0;
+  // option "kernel_profile": the LJ tile force kernels add up, per CTA, the clocks until the halo window is staged and
+  // the clocks of the whole CTA (queries "stage_clocks", "cta_clocks", "cta_count")
+  bool kernel_profile = false;
+  unsigned long long* d_prof = nullptr;
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_int = nullptr, ev_bnd = nullptr;
   std::set<const void*> smem_optin;  // kernels of this context's device already opted in to > 48 KB dynamic shared memory
@@ -244,7 +249,7 @@ struct mmd_ctx {
   // device scalars + pinned mirror
   // d_scal ints : [0] status, [1] max_n, [2] max_bin, [3] border total 0, [4] border total 1, [5] scan total,
   //               [6..9] exchange/border counts, [10] max full row, [11] max halo window, [12] tile status,
-  //               [13] tile row counter, [14] max rows of a tile, [16] interior tiles, [17] boundary tiles
+  //               [13] tile row counter, [14] max rows of a tile, [16] interior tiles, [17] boundary tiles, [18] all
   // d_ev doubles: [0] eng, [1] virial, [2] sum m v^2, [3] embed energy
   int* d_scal = nullptr;
   unsigned long long* d_total = nullptr;
@@ -708,7 +713,7 @@ template <class T> struct Impl {
   c->x.as<V>(), c->nlocal, c->bin_start.as<int>(), c->tile_slots.as<int>(), c->mbins, c->sruns.as<StencilRun>(), c->nsruns, \
       c->cutneighsq.as<T>(), c->ntypes, g, B, c->tile_runs.as<int2>(), c->tile_center.as<int4>(), c->tile_info.as<int2>(),  \
       c->trows.as<unsigned short>(), c->tcap, c->numneigh.as<int>(), c->tnum.as<int2>(), c->d_scal + 12, c->d_scal + 1,    \
-      c->d_scal + 10, c->d_total
+      c->d_scal + 10, c->d_total, (int)c->tile_pair_build
         if (B.uniform_cut) {
           if (mode == 0) LAUNCH_SMEM(c, (neigh_build_tile3_kernel<T, 0, 1>), g.ntiles, TB2_THREADS, b3_smem, NB3_ARGS);
           if (mode == 1) LAUNCH_SMEM(c, (neigh_build_tile3_kernel<T, 1, 1>), g.ntiles, TB2_THREADS, b3_smem, NB3_ARGS);
@@ -777,17 +782,19 @@ template <class T> struct Impl {
         c->list_dealt = true;
         c->xs_valid = false;
         MM(xs_fill(c));
-        c->split_ready = false;
-        if (c->nranks > 1 && c->split_enable && c->stream2) {
-          MM(c->tile_split.reserve((size_t)2 * g.ntiles * sizeof(int), c->stream));
-          CU(cudaMemsetAsync(c->d_scal + 16, 0, 2 * sizeof(int), c->stream));
+        // lists of the tiles that own local atoms (what the force kernels launch over): interior (no ghost in the halo
+        // window), boundary, and all of them
+        {
+          MM(c->tile_split.reserve((size_t)3 * g.ntiles * sizeof(int), c->stream));
+          CU(cudaMemsetAsync(c->d_scal + 16, 0, 3 * sizeof(int), c->stream));
           LAUNCH(c, tile_classify_kernel, div_up(g.ntiles, 4), 128, g, c->tile_runs.as<int2>(), c->tile_info.as<int2>(),
                  c->tile_slots.as<int>(), c->nlocal, c->tile_split.as<int>(), c->d_scal + 16);
-          CU(cudaMemcpyAsync(c->h_scal + 16, c->d_scal + 16, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+          CU(cudaMemcpyAsync(c->h_scal + 16, c->d_scal + 16, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
           CU(cudaStreamSynchronize(c->stream));
           c->n_interior = c->h_scal[16];
           c->n_boundary = c->h_scal[17];
-          c->split_ready = true;
+          c->n_active = c->h_scal[18];
+          c->split_ready = c->nranks > 1 && c->split_enable && c->stream2 != nullptr;
         }
       }
     }
@@ -918,13 +925,13 @@ template <class T> struct Impl {
       Q.cutforcesq_tab = P.cutforcesq_tab; Q.sigma6_tab = P.sigma6_tab; Q.epsilon_tab = P.epsilon_tab;
       Q.ntypes = P.ntypes; Q.e_scale = P.e_scale; Q.v_scale = P.v_scale;
       MM(smem_optin(c, force_lj_dealt_kernel<T, EV, UNI, INTEG>));
-      const int* list = part == 0 ? (const int*)nullptr : c->tile_split.as<int>() + (part == 2 ? g.ntiles : 0);
-      const int grid = part == 0 ? g.ntiles : (part == 1 ? c->n_interior : c->n_boundary);
+      const int* list = c->tile_split.as<int>() + (part == 0 ? 2 * g.ntiles : (part == 2 ? g.ntiles : 0));
+      const int grid = part == 0 ? c->n_active : (part == 1 ? c->n_interior : c->n_boundary);
       LAUNCH_ON(c, part == 1 ? c->stream2 : c->stream, (force_lj_dealt_kernel<T, EV, UNI, INTEG>), grid, TILE_THREADS,
                 qwin_smem_bytes<T>(g.hcap, !UNI, scap), c->x.as<V>(), c->f.as<V>(), g, c->tile_runs.as<int2>(),
                 c->tile_center.as<int4>(), c->tile_info.as<int2>(), mirror(c, c->xs_cur), c->xs_types.as<unsigned char>(),
                 c->trowsq.as<unsigned long long>(), c->tnum.as<int2>(), c->tcapq, c->nlocal, scap, Q, VP,
-                mirror(c, c->xs_cur ^ 1), c->d_ev, list);
+                mirror(c, c->xs_cur ^ 1), c->d_ev, list, c->kernel_profile ? c->d_prof : (unsigned long long*)nullptr);
       // the epilogue wrote the local atoms' new positions into the other mirror buffer (ghosts follow with the next
       // forward halo, as in x_alt); with a split launch the buffers flip once, after the second part
       if (INTEG && part != 1) c->xs_cur ^= 1;
@@ -934,7 +941,8 @@ template <class T> struct Impl {
     MM(smem_optin(c, force_lj_tile_kernel<T, EV, UNI, INTEG>));
     LAUNCH_SMEM(c, (force_lj_tile_kernel<T, EV, UNI, INTEG>), g.ntiles, TILE_THREADS, smem, c->x.as<V>(), c->f.as<V>(), g,
                 c->tile_runs.as<int2>(), c->tile_center.as<int4>(), c->tile_info.as<int2>(), c->tile_slots.as<int>(),
-                c->trows.as<unsigned short>(), c->tnum.as<int2>(), c->tcap, c->nlocal, P, VP, c->d_ev);
+                c->trows.as<unsigned short>(), c->tnum.as<int2>(), c->tcap, c->nlocal, P, VP, c->d_ev,
+                c->kernel_profile ? c->d_prof : (unsigned long long*)nullptr);
     return MMD_OK;
   }
   // force of step n + finalIntegrate(n) + initialIntegrate(n+1) in one launch (tile-resident lists only); the new
@@ -1837,6 +1845,7 @@ int mmd_ctx_destroy(mmd_ctx* c) {
     if (c->peer_win[r] && c->peer_win[r] != c->win) cudaIpcCloseMemHandle(c->peer_win[r]);
   if (c->win) cudaFree(c->win);
   if (c->d_done) cudaFree(c->d_done);
+  if (c->d_prof) cudaFree(c->d_prof);
 #ifdef MMD_WITH_NCCL
   if (c->nccl) ncclCommDestroy(c->nccl);
 #endif
@@ -2308,6 +2317,14 @@ int mmd_query_int(mmd_ctx* c, const char* key, long long* value) {
   else if (k == "list_dealt") *value = c->list_tile && c->list_dealt;
   else if (k == "tile_dealt_capacity") *value = c->tcapq;
   else if (k == "split_steps") *value = c->split_steps;
+  else if (k == "stage_clocks" || k == "cta_clocks" || k == "cta_count") {
+    unsigned long long h[4] = {0, 0, 0, 0};
+    if (c->d_prof) {
+      cudaStreamSynchronize(c->stream);
+      cudaMemcpy(h, c->d_prof, sizeof h, cudaMemcpyDeviceToHost);
+    }
+    *value = (long long)h[k == "stage_clocks" ? 0 : (k == "cta_clocks" ? 1 : 2)];
+  }
   else if (k == "tile_interior") *value = c->split_ready ? c->n_interior : 0;
   else if (k == "tile_boundary") *value = c->split_ready ? c->n_boundary : 0;
   else if (k == "tile_ok") *value = c->tile_ok;
@@ -2338,9 +2355,17 @@ int mmd_set_option(mmd_ctx* c, const char* key, long long value) {
     if (!c->fuse_halo) c->ghosts_resolved = false;
   } else if (k == "tile_dealt") {  // 1: the LJ force kernel walks bank-dealt rows (quarter warp per atom); 0: one lane pair per row
     c->tile_dealt = value != 0;     // takes effect at the next neighbor build
+  } else if (k == "kernel_profile") {
+    if (value && !c->d_prof) {
+      if (cudaMalloc(&c->d_prof, 4 * sizeof(unsigned long long)) != cudaSuccess) return set_err(MMD_ERR_CUDA, "kernel_profile: cudaMalloc");
+    }
+    if (c->d_prof) cudaMemset(c->d_prof, 0, 4 * sizeof(unsigned long long));
+    c->kernel_profile = value != 0;
   } else if (k == "split_force") {  // several ranks: interior tiles on a second stream behind the forward halo
     c->split_enable = value != 0;
     if (!c->split_enable) c->split_ready = false;
+  } else if (k == "tile_pair_build") {
+    c->tile_pair_build = value != 0;
   } else if (k == "tile_lane_build") {
     c->tile_lane_build = value != 0;
   } else if (k == "tile_xsort") {

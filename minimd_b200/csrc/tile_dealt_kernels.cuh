@@ -88,24 +88,42 @@ tile_rows_deal_kernel(const unsigned short* __restrict__ rows, const int2* __res
   }
   __syncthreads();
   if (n > 0) {
-    const unsigned short* __restrict__ src = reinterpret_cast<const unsigned short*>(s_src + threadIdx.x * sstride);
-    // class counts, 8 bits each (n <= 255)
-    unsigned long long cnt = 0ull;
-    for (int k = 0; k < n; k++) cnt += 1ull << ((src[k] & 7u) * 8u);
+    // class counts, 8 bits each (n <= 255): classes 0-3 in c0, 4-7 in c1; two entries per shared-memory word
+    const unsigned* __restrict__ srcw = s_src + threadIdx.x * sstride;
+    unsigned c0 = 0u, c1 = 0u;
+    const int nw2 = (n + 1) >> 1;
+    for (int k = 0; k < nw2; k++) {
+      const unsigned wd = srcw[k];
+      const unsigned i0 = 1u << ((wd & 3u) << 3), i1 = 1u << (((wd >> 16) & 3u) << 3);
+      const bool two = 2 * k + 1 < n;
+      c0 += (wd & 4u) ? 0u : i0;
+      c1 += (wd & 4u) ? i0 : 0u;
+      c0 += (two && !(wd & 0x40000u)) ? i1 : 0u;
+      c1 += (two && (wd & 0x40000u)) ? i1 : 0u;
+    }
     // exclusive prefix over the classes (byte k of the product = sum of the bytes below k; totals < 256)
-    unsigned long long pre = cnt * 0x0101010101010100ull;
+    unsigned p0 = c0 * 0x01010100u;
+    unsigned p1 = c1 * 0x01010100u + ((c0 * 0x01010101u) >> 24) * 0x01010101u;
     const int G = (n + QL - 1) / QL;
     const float rG = 1.0f / (float)G;
     unsigned short* dst = reinterpret_cast<unsigned short*>(s_dst + threadIdx.x * dstride);
-    for (int k = 0; k < n; k++) {
-      const unsigned ent = src[k];
-      const unsigned sh = (ent & 7u) * 8u;
-      const int t = (int)((pre >> sh) & 0xffull);
-      pre += 1ull << sh;
+    auto place = [&](unsigned ent) {
+      const unsigned sh = (ent & 3u) << 3;
+      const bool hi = (ent & 4u) != 0u;
+      const unsigned pre = hi ? p1 : p0;
+      const int t = (int)((pre >> sh) & 0xffu);
+      const unsigned inc = 1u << sh;
+      p0 += hi ? 0u : inc;
+      p1 += hi ? inc : 0u;
       // t / G for t < 256: (t + 0.5) / G stays >= 0.5 / G away from every integer, far above the FP32 error
       const int p = __float2int_rd(((float)t + 0.5f) * rG);
       const int g = t - p * G;
-      dst[(g >> 2) * QBLK + p * QB + (g & 3)] = (unsigned short)ent;   // the half-list flag (bit 15) travels along
+      dst[((g >> 2) << 5) + (p << 2) + (g & 3)] = (unsigned short)ent;   // the half-list flag (bit 15) travels along
+    };
+    for (int k = 0; k < nw2; k++) {
+      const unsigned wd = srcw[k];
+      place(wd & 0xffffu);
+      if (2 * k + 1 < n) place(wd >> 16);
     }
   }
   __syncthreads();
@@ -306,98 +324,93 @@ force_lj_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Ti
                       const unsigned char* __restrict__ types_s, const unsigned long long* __restrict__ rowsq,
                       const int2* __restrict__ row_atom, int tcapq, int nlocal, int scap, LJDealtParams<T> P,
                       VerletParams<T> VP, XsMirror<T> xs_out, double* __restrict__ ev_out,
-                      const int* __restrict__ tile_list /* nullptr: every tile, blockIdx.x = tile */) {
+                      const int* __restrict__ tile_list /* nullptr: every tile, blockIdx.x = tile */,
+                      unsigned long long* __restrict__ prof /* {staging clocks, CTA clocks, CTAs}: -DMMD_KERNEL_PROFILE builds only */) {
   extern __shared__ __align__(16) unsigned char tile_smem_raw[];
-  const int t = tile_list ? __ldg(tile_list + blockIdx.x) : blockIdx.x;
-  const int2 inf = tile_info[t];
-  if (inf.y == 0) return;
+  // tile_list holds tiles that own local atoms only (tile_classify_kernel): no CTA exits early, and nothing has to
+  // be read from global memory before the copies of the window can be described
+  const int t = __ldg(tile_list + blockIdx.x);
+#ifdef MMD_KERNEL_PROFILE
+  const long long clk0 = clock64();
+#endif
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
   const int p = lane & (QL - 1), qg = lane >> 3;
   const int wpr = tcapq / QB;  // 64-bit words per row
-  const int H = inf.x;
   const unsigned long long sent4 = 0x0001000100010001ull * (unsigned long long)(g.hcap - 8 + p);  // lane p's sentinel
 
   QWin<T> S;
   S.carve(tile_smem_raw, g.hcap, scap);
 
-  // ---- phase 1: tables, then the asynchronous copies ----
-  const int2* tr = tile_runs + (size_t)t * g.nrun;
-  int2 my_run = make_int2(0, 0);
-  int my_len = 0;
-  if (tid < g.nrun) {
-    my_run = __ldg(tr + tid);
-    my_len = (tid + 1 < g.nrun ? __ldg(tr + tid + 1).y : H) - my_run.y;
-    S.run_start[tid] = my_run.x;
-    S.run_off[tid] = my_run.y;
-  }
-  if (tid == 0) {
-    S.run_off[g.nrun] = H;
-    mbar_init(S.bar, 1);
-  }
+  // ---- phase 1: the asynchronous copies of the halo window.  One barrier up front (mbarrier visible to everybody, no
+  //      load in flight yet); after that every thread describes and issues its copies as soon as ITS table entries
+  //      arrive -- one round trip for the tables, one for the data, no barrier in between ----
+  if (tid == 0) mbar_init(S.bar, 1);
   if (tid >= 32 && tid < 40) {  // the eight sentinel atoms, one per bank class
     Vec4<T> far;
     far.x = far.y = far.z = sentinel_coord<T>();
     far.w = type_to_lane<T>(0);
     S.put(g.hcap - 40 + tid, far, !UNIFORM);
   }
-  if (w == 0) {  // centre pencils: lanes 0..15
-    int4 ce = make_int4(0, 0, 0, 0);
-    int slot0 = 0;
-    if (lane < TILE_NCENTER) {
-      ce = __ldg(tile_center + (size_t)t * TILE_NCENTER + lane);
-      const int2 r = __ldg(tr + (lane % TBY + g.sy) + (lane / TBY + g.sz) * g.nry);
-      slot0 = r.x - r.y;
-    }
-    const int n = ce.y - ce.x;
-    const int np = (n + 3) >> 2;
-    int incl = np;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane < TILE_NCENTER) {
-      S.pc[lane] = make_int4(ce.x, n, ce.z, slot0);
-      S.pp[lane] = incl - np;
-    }
-    if (lane == TILE_NCENTER) S.pp[TILE_NCENTER] = incl;  // lanes >= 16 add nothing: incl = total
-  }
   __syncthreads();
-  if (tid == 0) mbar_expect_tx(S.bar, (unsigned)H * 16u);
-  if (my_len > 0) bulk_g2s(S.rec + my_run.y, xs_in.rec + my_run.x, (unsigned)my_len * 16u, S.bar);
-  if constexpr (sizeof(T) == 8) {
+  const int2* tr = tile_runs + (size_t)t * g.nrun;
+  const int4* tc = tile_center + (size_t)t * TILE_NCENTER;
+  if (tid < g.nrun) {  // thread r: pencil run r of the window, ONE bulk copy of 16-byte records
+    const int2 my_run = __ldg(tr + tid);
+    const int my_len = (tid + 1 < g.nrun ? __ldg(tr + tid + 1).y : __ldg(tc).w) - my_run.y;
+    if (tid == 0) mbar_expect_tx(S.bar, (unsigned)__ldg(tc).w * 16u);  // tile_center[0].w = atoms of the window
+    if (my_len > 0) bulk_g2s(S.rec + my_run.y, xs_in.rec + my_run.x, (unsigned)my_len * 16u, S.bar);
+  }
+  if constexpr (sizeof(T) == 8) {  // FP64: z values (8-byte cp.async), run tables read straight from global
     for (int r = w; r < g.nrun; r += nw) {
-      const int start = S.run_start[r], off = S.run_off[r], len = S.run_off[r + 1] - off;
+      const int2 r0 = __ldg(tr + r);
+      const int len = (r + 1 < g.nrun ? __ldg(tr + r + 1).y : __ldg(tc).w) - r0.y;
       for (int k = lane; k < len; k += 32) {
-        cp_async8(S.z + off + k, xs_in.z + start + k);
-        if (!UNIFORM) S.st[off + k] = __ldg(types_s + start + k);
+        cp_async8(S.z + r0.y + k, xs_in.z + r0.x + k);
+        if (!UNIFORM) S.st[r0.y + k] = __ldg(types_s + r0.x + k);
       }
     }
   }
 
-  // pass list: pass i of the tile belongs to the pencil c with pp[c] <= i < pp[c+1]
-  const int NP = S.pp[TILE_NCENTER];
-  const int my_end = lane < TILE_NCENTER ? S.pp[lane + 1] : 0x7fffffff;
-  const int qtile0 = S.pc[0].z;
+  // centre pencils, held by EVERY warp in the registers of lanes 0..15: {first tile-local index, atoms, first row,
+  // CSR slot of tile-local index 0} and the exclusive prefix of the pencils' pass counts
+  int4 pcl = make_int4(0, 0, 0, 0);
+  if (lane < TILE_NCENTER) {
+    const int4 ce = __ldg(tc + lane);
+    const int2 r = __ldg(tr + (lane % TBY + g.sy) + (lane / TBY + g.sz) * g.nry);
+    pcl = make_int4(ce.x, ce.y - ce.x, ce.z, r.x - r.y);
+  }
+  const int np_l = (pcl.y + 3) >> 2;
+  int my_end = np_l;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, my_end, o);
+    if (lane >= o) my_end += v;
+  }
+  const int NP = __shfl_sync(0xffffffffu, my_end, 31);
+  const int my_beg = my_end - np_l;
+  if (lane >= TILE_NCENTER) my_end = 0x7fffffff;
+  const int qtile0 = __shfl_sync(0xffffffffu, pcl.z, 0);
+  const int nrows = __shfl_sync(0xffffffffu, pcl.z + pcl.y, TILE_NCENTER - 1) - qtile0;
+  if (w == 0 && lane < TILE_NCENTER) S.pc[lane] = pcl;  // for the epilogue (read after the barriers below)
+
+  // pass list: pass i of the tile belongs to the pencil c with beg[c] <= i < end[c]
   int2 ta_n = make_int2(-1, 0);
   unsigned long long w_n = sent4;
   int a_n = 0, q_n = 0, c_n = 0;
   bool have_n = false;
   auto locate = [&](int i) {  // fills the *_n state for pass i (warp-uniform i)
-    c_n = __popc(__ballot_sync(0xffffffffu, my_end <= i));
-    have_n = false;
+    c_n = min(__popc(__ballot_sync(0xffffffffu, my_end <= i)), TILE_NCENTER - 1);
+    const int lo = __shfl_sync(0xffffffffu, pcl.x, c_n), cnt = __shfl_sync(0xffffffffu, pcl.y, c_n);
+    const int q0 = __shfl_sync(0xffffffffu, pcl.z, c_n), beg = __shfl_sync(0xffffffffu, my_beg, c_n);
+    const int k = (i - beg) * 4 + qg;
+    have_n = i < NP && k < cnt;
     ta_n = make_int2(-1, 0);
     w_n = sent4;
-    if (i < NP) {
-      const int4 pc = S.pc[c_n];
-      const int k = (i - S.pp[c_n]) * 4 + qg;
-      have_n = k < pc.y;
-      a_n = pc.x + (have_n ? k : 0);
-      q_n = pc.z + (have_n ? k : 0);
-      if (have_n) {
-        ta_n = __ldg(row_atom + q_n);
-        w_n = ldg_rowq(rowsq + (size_t)q_n * wpr + p);
-      }
+    a_n = lo + (have_n ? k : 0);
+    q_n = q0 + (have_n ? k : 0);
+    if (have_n) {
+      ta_n = __ldg(row_atom + q_n);
+      w_n = ldg_rowq(rowsq + (size_t)q_n * wpr + p);
     }
   };
   locate(w);
@@ -405,6 +418,9 @@ force_lj_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Ti
   if constexpr (sizeof(T) == 8) cp_async_wait_all();
   mbar_wait(S.bar, 0);
   __syncthreads();
+#ifdef MMD_KERNEL_PROFILE
+  const long long clk1 = clock64();
+#endif
 
   // ---- phase 2: the passes ----
   double eng = 0.0, vir = 0.0, ke = 0.0;
@@ -458,7 +474,6 @@ force_lj_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Ti
   __syncthreads();
 
   // ---- phase 3: one thread per row of the tile ----
-  const int nrows = S.pc[TILE_NCENTER - 1].z + S.pc[TILE_NCENTER - 1].y - qtile0;
   for (int j = tid; j < nrows; j += blockDim.x) {
     const int2 ta = __ldg(row_atom + (size_t)(qtile0 + j));
     if (ta.x < 0 || ta.x >= nlocal) continue;
@@ -501,12 +516,23 @@ force_lj_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Ti
       block_accumulate<2>(v2, ev_out);
     }
   }
+#ifdef MMD_KERNEL_PROFILE
+  if (prof) {
+    __syncthreads();
+    if (tid == 0) {
+      atomicAdd(prof + 0, (unsigned long long)(clk1 - clk0));
+      atomicAdd(prof + 1, (unsigned long long)(clock64() - clk0));
+      atomicAdd(prof + 2, 1ull);
+    }
+  }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------
 // Interior / boundary split for several ranks: a tile whose halo window holds no ghost atom needs nothing from the
 // forward halo, so its force can run while the halo of the same step is still in flight.  One warp per tile scans the
-// window's slots; lists[0 .. counts[0]) receives the interior tiles, lists[ntiles .. ntiles + counts[1]) the others.
+// window's slots; lists[0 .. counts[0]) receives the interior tiles, lists[ntiles .. ntiles + counts[1]) the others,
+// lists[2*ntiles .. 2*ntiles + counts[2]) every tile that owns local atoms (what a single launch covers).
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 tile_classify_kernel(TileGeo g, const int2* __restrict__ tile_runs, const int2* __restrict__ tile_info,
@@ -529,6 +555,7 @@ tile_classify_kernel(TileGeo g, const int2* __restrict__ tile_runs, const int2* 
   if (lane == 0) {
     const int k = atomicAdd(counts + (ghost ? 1 : 0), 1);
     lists[(ghost ? g.ntiles : 0) + k] = t;
+    lists[2 * g.ntiles + atomicAdd(counts + 2, 1)] = t;
   }
 }
 

@@ -127,7 +127,8 @@ tile_table_kernel(TileGeo g, const int* __restrict__ bin_start, const int* __res
     atomicMax(max_rows, tile_rows);
   }
   base = __shfl_sync(0xffffffffu, base, 0);
-  if (lane < TILE_NCENTER) center[(size_t)t * TILE_NCENTER + lane] = make_int4(lo, hi, any ? base + incl - len_c : 0, 0);
+  // .w: atoms of the halo window (-1: the tile owns no local atom)
+  if (lane < TILE_NCENTER) center[(size_t)t * TILE_NCENTER + lane] = make_int4(lo, hi, any ? base + incl - len_c : 0, any ? carry : -1);
   if (lane == 0) {
     info[t] = make_int2(carry, any ? 1 : 0);
     if (any) atomicMax(max_h, carry);
@@ -349,7 +350,7 @@ __device__ __noinline__ bool build2_ghost_below(const Vec4<T>* __restrict__ x, i
 }
 
 template <class T, int MODE, int UC>
-__global__ void __launch_bounds__(TB2_THREADS, 3)
+__global__ void __launch_bounds__(TB2_THREADS, 4)
 neigh_build_tile2_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* __restrict__ bin_start,
                          const int* __restrict__ bin_atoms, int mbins, const StencilRun* __restrict__ sruns, int nsr,
                          const T* __restrict__ cutneighsq, int ntypes, TileGeo g, Build2Params<T> B,
@@ -744,7 +745,8 @@ neigh_build_tile3_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* _
                          const int2* __restrict__ tile_runs, const int4* __restrict__ tile_center,
                          const int2* __restrict__ tile_info, unsigned short* __restrict__ rows, int tcap,
                          int* __restrict__ numneigh_half, int2* __restrict__ row_atom, int* __restrict__ status,
-                         int* __restrict__ max_half, int* __restrict__ max_full, unsigned long long* __restrict__ total_half) {
+                         int* __restrict__ max_half, int* __restrict__ max_full, unsigned long long* __restrict__ total_half,
+                         int pair /* 1: two atoms of a bin per sweep */) {
   extern __shared__ __align__(16) unsigned char b3_smem[];
   const int t = blockIdx.x;
   const int2 inf = tile_info[t];
@@ -846,25 +848,42 @@ neigh_build_tile3_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* _
       }
       const bool bad_geom = __any_sync(0xffffffffu, r_whi == -2);
 
-      for (int a = own_lo; a < own_hi; a++) {
-        const int id_i = __ldg(slots + slot0_c + a);
-        if (id_i >= nlocal) continue;  // warp-uniform
+      // ---- the local atoms of the bin, TWO at a time: consecutive atoms of an x-sorted bin have almost the same
+      //      candidates, so the pair shares one interval search per run (the union of the two intervals) and every
+      //      sweep of 32 candidates is fetched once and tested against both ----
+      for (int a = own_lo; a < own_hi;) {
+        const int idA = __ldg(slots + slot0_c + a);
+        if (idA >= nlocal) { a++; continue; }  // warp-uniform
+        int idB = 0x7fffffff;
+        if (pair && a + 1 < own_hi) idB = __ldg(slots + slot0_c + a + 1);
+        const bool two = idB < nlocal;
+        const int aA = a, aB = two ? a + 1 : a;
+        a += two ? 2 : 1;
         if (bad_geom) { if (lane == 0) atomicOr(status, 2); continue; }
-        const float xi = sx[a], yi = sy[a], zi = sz[a];
-        const int ti = UC ? 0 : (int)st[a];
-        const int q = ce.z + (a - ce.x);
-        unsigned short* rowp = rows + (size_t)q * tcap;
+        const float xA = sx[aA], yA = sy[aA], zA = sz[aA], xB = sx[aB], yB = sy[aB], zB = sz[aB];
+        const int tA = UC ? 0 : (int)st[aA], tB = UC ? 0 : (int)st[aB];
+        const int qA = ce.z + (aA - ce.x), qB = ce.z + (aB - ce.x);
+        unsigned short* rowA = rows + (size_t)qA * tcap;
+        unsigned short* rowB = rows + (size_t)qB * tcap;
 
-        // ---- this atom's candidate interval in every run ----
+        // ---- candidate interval of the pair in every run ----
         int L = 0, len = 0;
         if (lane < nsr && r_whi >= 0) {
-          const float gy = fmaxf(0.0f, fmaxf(r_ylo - yi, yi - (r_ylo + bsy)));
-          const float gz = fmaxf(0.0f, fmaxf(r_zlo - zi, zi - (r_zlo + bsz)));
-          const float rem = rc2 - gy * gy - gz * gz;
-          if (rem > 0.0f) {
-            const float xr = sqrtf(rem);
+          float xa = 3.0e38f, xb = -3.0e38f;
+          {
+            const float gy = fmaxf(0.0f, fmaxf(r_ylo - yA, yA - (r_ylo + bsy)));
+            const float gz = fmaxf(0.0f, fmaxf(r_zlo - zA, zA - (r_zlo + bsz)));
+            const float rem = rc2 - gy * gy - gz * gz;
+            if (rem > 0.0f) { const float xr = sqrtf(rem); xa = xA - xr; xb = xA + xr; }
+          }
+          if (two) {
+            const float gy = fmaxf(0.0f, fmaxf(r_ylo - yB, yB - (r_ylo + bsy)));
+            const float gz = fmaxf(0.0f, fmaxf(r_zlo - zB, zB - (r_zlo + bsz)));
+            const float rem = rc2 - gy * gy - gz * gz;
+            if (rem > 0.0f) { const float xr = sqrtf(rem); xa = fminf(xa, xB - xr); xb = fmaxf(xb, xB + xr); }
+          }
+          if (xa <= xb) {
             const int lo_i = s_binoff[r_row + r_wlo], hi_i = s_binoff[r_row + r_whi];
-            const float xa = xi - xr, xb = xi + xr;
             int l0 = lo_i, l1 = hi_i;  // first index with sx >= xa
             while (l0 < l1) {
               const int mid = (l0 + l1) >> 1;
@@ -894,11 +913,11 @@ neigh_build_tile3_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* _
         __syncwarp();
         const int my_dpref = lane < nd ? dense[lane].y : 0x7fffffff;
 
-        int n_t = 0, h_t = 0;
-        // one pass over the atom's candidates, 32 per sweep; EXACT adds the FP64 re-test of candidates inside the guard band
+        int nA = 0, hA = 0, nB = 0, hB = 0;
+        // one pass over the pair's candidates, 32 per sweep; EXACT adds the FP64 re-test of candidates inside the guard band
         auto sweep_all = [&](auto exact_tag) -> bool {
           constexpr bool EXACT = decltype(exact_tag)::value;
-          n_t = 0; h_t = 0;
+          nA = 0; hA = 0; nB = 0; hB = 0;
           bool closeany = false;
           const unsigned own_n = (unsigned)(own_hi - own_lo);
           for (int s0 = 0; s0 < M; s0 += 32) {
@@ -909,66 +928,106 @@ neigh_build_tile3_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* _
             const int before = __popc(__ballot_sync(0xffffffffu, my_dpref < s0));
             const int rr = valid ? before + __popc(starts & ((2u << lane) - 1u)) - 1 : 0;
             const int4 dv = dense[rr];
-            const int lc = valid ? dv.x + n : a;
+            const int lc = valid ? dv.x + n : aA;
             const int info = dv.z;
-            const float dx = xi - sx[lc], dy = yi - sy[lc], dz = zi - sz[lc];
-            T cut = B.cut0;
-            float fc = fcut0;
-            if (!UC) { cut = __ldg(&cutneighsq[ti * ntypes + (int)st[lc]]); fc = (float)cut; }
-            bool ok;
-            if (sizeof(T) == 4) {
-              ok = rsq_unfused(dx, dy, dz) <= fc;
-            } else {
-              const float d = (dx * dx + dy * dy + dz * dz) - fc;
-              ok = d < -band;
-              const bool close = fabsf(d) <= band && lc != a;
-              if (!EXACT) closeany = closeany || close;
-              if (EXACT) {
-                if (__any_sync(0xffffffffu, close && valid)) {
-                  if (close && valid) ok = build2_exact_within<T>(x, id_i, __ldg(slots + (info >> 2) + lc), cut);
+            const float cxj = sx[lc], cyj = sy[lc], czj = sz[lc];
+            T cutA = B.cut0, cutB = B.cut0;
+            float fA = fcut0, fB = fcut0;
+            if (!UC) {
+              const int tj = (int)st[lc];
+              cutA = __ldg(&cutneighsq[tA * ntypes + tj]); fA = (float)cutA;
+              cutB = __ldg(&cutneighsq[tB * ntypes + tj]); fB = (float)cutB;
+            }
+            bool okA, okB;
+            {
+              const float dx = xA - cxj, dy = yA - cyj, dz = zA - czj;
+              if (sizeof(T) == 4) {
+                okA = rsq_unfused(dx, dy, dz) <= fA;
+              } else {
+                const float d = (dx * dx + dy * dy + dz * dz) - fA;
+                okA = d < -band;
+                const bool close = fabsf(d) <= band && lc != aA && valid;
+                if (!EXACT) closeany = closeany || close;
+                if (EXACT) {
+                  if (__any_sync(0xffffffffu, close)) {
+                    if (close) okA = build2_exact_within<T>(x, idA, __ldg(slots + (info >> 2) + lc), cutA);
+                  }
                 }
               }
             }
-            ok = ok && valid && lc != a;
-            bool half = true;
+            {
+              const float dx = xB - cxj, dy = yB - cyj, dz = zB - czj;
+              if (sizeof(T) == 4) {
+                okB = rsq_unfused(dx, dy, dz) <= fB;
+              } else {
+                const float d = (dx * dx + dy * dy + dz * dz) - fB;
+                okB = d < -band;
+                const bool close = two && fabsf(d) <= band && lc != aB && valid;
+                if (!EXACT) closeany = closeany || close;
+                if (EXACT) {
+                  if (__any_sync(0xffffffffu, close)) {
+                    if (close) okB = build2_exact_within<T>(x, idB, __ldg(slots + (info >> 2) + lc), cutB);
+                  }
+                }
+              }
+            }
+            okA = okA && valid && lc != aA;
+            okB = okB && valid && lc != aB && two;
+            bool halfA = true, halfB = true;
             if (MODE == 1) {
               const bool own_bin = (info & 1) && (unsigned)(lc - own_lo) < own_n;
-              half = (info & 2) != 0 || ((info & 1) && lc >= own_hi);
-              if (__any_sync(0xffffffffu, own_bin && ok)) {  // within the bin the reference orders by atom id
-                if (own_bin && ok) {
+              halfA = halfB = (info & 2) != 0 || ((info & 1) && lc >= own_hi);
+              if (__any_sync(0xffffffffu, own_bin && (okA || okB))) {  // within the bin the reference orders by atom id
+                if (own_bin && (okA || okB)) {
                   const int id_j = __ldg(slots + slot0_c + lc);
-                  half = id_j > id_i;
-                  if (half && id_j >= nlocal) half = !build2_ghost_below<T>(x, id_i, id_j);
+                  halfA = id_j > idA;
+                  if (halfA && okA && id_j >= nlocal) halfA = !build2_ghost_below<T>(x, idA, id_j);
+                  halfB = id_j > idB;
+                  if (halfB && okB && id_j >= nlocal) halfB = !build2_ghost_below<T>(x, idB, id_j);
                 }
               }
             }
             if (MODE == 2) {
-              half = false;
-              if (ok) half = __ldg(slots + (info >> 2) + lc) > id_i;
+              halfA = halfB = false;
+              if (okA || okB) {
+                const int id_j = __ldg(slots + (info >> 2) + lc);
+                halfA = id_j > idA;
+                halfB = id_j > idB;
+              }
             }
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            const unsigned mh = MODE == 0 ? m : __ballot_sync(0xffffffffu, ok && half);
-            if (ok) {
-              const int pos = n_t + __popc(m & lt_mask);
-              if (pos < tcap) rowp[pos] = (unsigned short)(lc | ((MODE != 0 && half) ? TILE_HALF_BIT : 0));
+            const unsigned mA = __ballot_sync(0xffffffffu, okA);
+            const unsigned mB = __ballot_sync(0xffffffffu, okB);
+            const unsigned mhA = MODE == 0 ? mA : __ballot_sync(0xffffffffu, okA && halfA);
+            const unsigned mhB = MODE == 0 ? mB : __ballot_sync(0xffffffffu, okB && halfB);
+            if (okA) {
+              const int pos = nA + __popc(mA & lt_mask);
+              if (pos < tcap) rowA[pos] = (unsigned short)(lc | ((MODE != 0 && halfA) ? TILE_HALF_BIT : 0));
             }
-            n_t += __popc(m);
-            h_t += __popc(mh);
+            if (okB) {
+              const int pos = nB + __popc(mB & lt_mask);
+              if (pos < tcap) rowB[pos] = (unsigned short)(lc | ((MODE != 0 && halfB) ? TILE_HALF_BIT : 0));
+            }
+            nA += __popc(mA); hA += __popc(mhA);
+            nB += __popc(mB); hB += __popc(mhB);
           }
           return __any_sync(0xffffffffu, closeany);
         };
         if (sizeof(T) == 4) {
           sweep_all(TileTag<false>());
         } else if (sweep_all(TileTag<false>())) {
-          sweep_all(TileTag<true>());  // a candidate sat inside the guard band: redo this atom with exact FP64 tests
+          sweep_all(TileTag<true>());  // a candidate sat inside the guard band: redo this pair with exact FP64 tests
         }
         if (lane == 0) {
-          numneigh_half[id_i] = h_t;
-          row_atom[q] = make_int2(id_i, n_t);
+          numneigh_half[idA] = hA;
+          row_atom[qA] = make_int2(idA, nA);
+          if (two) {
+            numneigh_half[idB] = hB;
+            row_atom[qB] = make_int2(idB, nB);
+          }
         }
-        warp_max_h = max(warp_max_h, h_t);
-        warp_max_f = max(warp_max_f, n_t);
-        if (lane == 0) warp_total += (unsigned long long)h_t;
+        warp_max_h = max(warp_max_h, max(hA, two ? hB : 0));
+        warp_max_f = max(warp_max_f, max(nA, two ? nB : 0));
+        if (lane == 0) warp_total += (unsigned long long)(hA + (two ? hB : 0));
       }
     }
   }
@@ -1098,11 +1157,15 @@ __global__ void __launch_bounds__(TILE_THREADS, 2)
 force_lj_tile_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, TileGeo g, const int2* __restrict__ tile_runs,
                      const int4* __restrict__ tile_center, const int2* __restrict__ tile_info, const int* __restrict__ slots,
                      const unsigned short* __restrict__ rows, const int2* __restrict__ row_atom, int tcap, int nlocal,
-                     LJTileParams<T> P, VerletParams<T> VP, double* __restrict__ ev_out) {
+                     LJTileParams<T> P, VerletParams<T> VP, double* __restrict__ ev_out,
+                     unsigned long long* __restrict__ prof /* {staging clocks, CTA clocks, CTAs}: -DMMD_KERNEL_PROFILE builds only */) {
   extern __shared__ __align__(16) unsigned char tile_smem_raw[];
   const int t = blockIdx.x;
   const int2 inf = tile_info[t];
   if (inf.y == 0) return;
+#ifdef MMD_KERNEL_PROFILE
+  const long long clk0 = clock64();
+#endif
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int sub = lane & (LJT_TPA - 1);
   constexpr int APP = 32 / LJT_TPA;  // atoms per pass of a warp
@@ -1126,6 +1189,9 @@ force_lj_tile_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Til
   TileSmem<T> S;
   S.carve(tile_smem_raw, g.hcap, !UNIFORM);
   tile_stage<T, !UNIFORM, true>(S, g, t, inf.x, tile_runs, slots, x);
+#ifdef MMD_KERNEL_PROFILE
+  const long long clk1 = clock64();
+#endif
   const Vec2<T>* __restrict__ sxy = reinterpret_cast<const Vec2<T>*>(S.sx);
 
   double eng = 0.0, vir = 0.0, ke = 0.0;
@@ -1256,6 +1322,16 @@ force_lj_tile_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Til
       block_accumulate<2>(v2, ev_out);
     }
   }
+#ifdef MMD_KERNEL_PROFILE
+  if (prof) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      atomicAdd(prof + 0, (unsigned long long)(clk1 - clk0));
+      atomicAdd(prof + 1, (unsigned long long)(clock64() - clk0));
+      atomicAdd(prof + 2, 1ull);
+    }
+  }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------

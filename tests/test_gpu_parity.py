@@ -51,19 +51,21 @@ CASES = [
 # ------------------------------------------------------------------------------------------
 # binning / borders / neighbor build / sort : bit-exact
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("tile", [1, 3, 2, 0])
+@pytest.mark.parametrize("tile", [1, 3, 4, 2, 0])
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 @pytest.mark.parametrize("steps", [0, 40])
 @pytest.mark.parametrize("case", range(len(CASES)))
 def test_borders_bins_and_lists_are_bit_exact(case, steps, prec, tile):
-    """tile=1: tile-resident 16-bit rows built on x-sorted windows, one lane per atom (the default), and exported back
-    to the reference's format; tile=3: the same with one warp per atom; tile=2: the same rows from the per-bin
-    candidate-table build (windows in CSR order); tile=0: classic rows."""
+    """tile=1: tile-resident 16-bit rows built on x-sorted windows by the interval build, two atoms of a bin per sweep
+    (the default), and exported back to the reference's format; tile=3: the same, one atom per sweep; tile=4: the same
+    rows from the one-lane-per-atom build; tile=2: from the per-bin candidate-table build (windows in CSR order);
+    tile=0: classic rows."""
     o = melted(CASES[case], steps, prec)
     c = context_from_oracle(o)
     c.set_option("tile_lists", 1 if tile else 0)
-    c.set_option("tile_xsort", 1 if tile in (1, 3) else 0)
-    c.set_option("tile_lane_build", 1 if tile == 1 else 0)
+    c.set_option("tile_xsort", 1 if tile in (1, 3, 4) else 0)
+    c.set_option("tile_pair_build", 0 if tile == 3 else 1)
+    c.set_option("tile_lane_build", 1 if tile == 4 else 0)
     c.exchange()
     c.borders()
     # ghosts: counts, send lists, positions (+- prd shifts) and types
@@ -89,7 +91,7 @@ def test_borders_bins_and_lists_are_bit_exact(case, steps, prec, tile):
     half, gn = o.geti("halfneigh"), o.geti("ghost_newton")
     mxn, total = c.build(half, gn, 100)
     assert c.query("list_tile") == (1 if tile else 0)
-    assert c.query("list_xsorted") == (1 if tile in (1, 3) else 0)
+    assert c.query("list_xsorted") == (1 if tile in (1, 3, 4) else 0)
     num, nb = c.neigh_download()
     onum, onb = o.numneigh(), o.neighbors()
     assert mxn == o.geti("maxneighs")
