@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Run every tests/test_gpu_multi.py case the visible GPUs allow and write the checker's JSON lines to one record
-(committed as profiles/r2_multi_rank_check.json): python tools/multi_rank_record.py OUT.json"""
+(committed as profiles/r2_multi_rank_check.json): python tools/multi_rank_record.py OUT.json [ranks]"""
 import json
 import os
 import sys
@@ -13,9 +13,12 @@ import torch  # noqa: E402
 from test_gpu_multi import CASES, launch  # noqa: E402
 
 n_avail = torch.cuda.device_count()
+only = int(sys.argv[2]) if len(sys.argv) > 2 else 0   # optional: run the cases of exactly this many ranks
 out = {"gpus_visible": n_avail, "gpu": torch.cuda.get_device_name(0) if n_avail else None, "cases": []}
 for k, (n, extra) in enumerate(CASES):
     rec = {"ranks": n, "args": [str(e) for e in extra]}
+    if only and n != only:
+        continue
     if n > n_avail:
         rec["skipped"] = f"needs {n} GPUs"
     else:
