@@ -219,11 +219,16 @@ int mmd_query_int(mmd_ctx* ctx, const char* key, long long* value);
  *   "fuse_integrate" (1)  mmd_run: finalIntegrate(n) + initialIntegrate(n+1) in one kernel
  *   "fuse_force" (1)      mmd_run, tile lists: ... and both inside the force kernel's epilogue
  *   "fuse_halo" (1)       one rank: forward halo in one launch (ghosts resolved to their local source)
+ *   "fuse_ghosts" (0)     one rank, dealt LJ lists: the fused force kernel also writes every atom's periodic images, so
+ *                         the forward halo of the next step needs no launch at all (measured slower: off by default)
  *   "p2p_halo" (1)        several ranks: forward halo over CUDA-IPC peer windows; 0 = NCCL send/recv
+ *   "split_force" (1)     several ranks, dealt LJ lists: tiles without ghosts in their halo window run on a second stream
+ *                         while the forward halo of the step is in flight; boundary tiles follow the halo
  *   "lj_threads_per_atom" (0 = auto), "eam_threads_per_atom" (8): lanes per atom of the classic kernels
  *   "phase_timing" (0)    per-phase CUDA-event timing of mmd_run
  * Queries added by these paths: "list_tile", "list_dealt", "list_xsorted", "tile_ok", "tile_builds", "tile_fallbacks",
- * "tile_max_halo", "tile_max_full", "tile_row_capacity", "tile_dealt_capacity", "tile_count", "p2p_active", "p2p_calls". */
+ * "tile_max_halo", "tile_max_full", "tile_row_capacity", "tile_dealt_capacity", "tile_count", "tile_interior",
+ * "tile_boundary", "split_steps", "fused_halo_steps", "p2p_active", "p2p_calls". */
 int mmd_set_option(mmd_ctx* ctx, const char* key, long long value);
 
 #ifdef __cplusplus

@@ -197,6 +197,7 @@ struct mmd_ctx {
   bool split_ready = false;   // tile_split holds the lists of the current neighbor list
   bool split_active = false;  // work may be pending on stream2 (joined before anything else touches the atoms)
   bool ev_int_valid = false;
+  DevBuf send_flag;           // [nlocal] 1: the atom is in a send list (its tile counts as boundary)
   DevBuf tile_split;          // [3 * ntiles] interior tiles | boundary tiles | all tiles that own local atoms
   int n_interior = 0, n_boundary = 0, n_active = 0;
   long long split_steps = 0;
@@ -229,6 +230,12 @@ struct mmd_ctx {
   DevBuf border_tiles;  // 2 arrays of tile counts
   DevBuf ghost_src, ghost_shift;  // single rank: every ghost resolved to its local source + periodic shift
   bool ghosts_resolved = false;
+  // ... inverted: the ghost images of every local atom (xs_mirror.cuh), written by the fused force kernel's epilogue
+  bool fuse_ghosts = false;       // option "fuse_ghosts" (measured slower than the separate halo launch at every size: off)
+  bool images_ready = false;      // img_* describe the current ghosts
+  bool ghosts_fresh = false;      // the last launch already wrote the ghosts of the next step
+  DevBuf img_start, img_cursor, img_list;
+  long long fused_halo_steps = 0;
   bool fuse_halo = true;          // option "fuse_halo"
   DevBuf sendbuf, recvbuf;
   DevBuf exch_flag, exch_pos, exch_holes;
@@ -787,8 +794,17 @@ template <class T> struct Impl {
         {
           MM(c->tile_split.reserve((size_t)3 * g.ntiles * sizeof(int), c->stream));
           CU(cudaMemsetAsync(c->d_scal + 16, 0, 3 * sizeof(int), c->stream));
-          LAUNCH(c, tile_classify_kernel, div_up(g.ntiles, 4), 128, g, c->tile_runs.as<int2>(), c->tile_info.as<int2>(),
-                 c->tile_slots.as<int>(), c->nlocal, c->tile_split.as<int>(), c->d_scal + 16);
+          const bool want_split = c->nranks > 1 && c->split_enable && c->stream2 != nullptr;
+          if (want_split) {  // atoms the forward halo reads: their tiles go to the boundary list
+            MM(c->send_flag.reserve((size_t)std::max(c->nlocal, 1), c->stream, 0, 1.2));
+            CU(cudaMemsetAsync(c->send_flag.p, 0, (size_t)std::max(c->nlocal, 1), c->stream));
+            for (int ws = 0; ws < c->swaps.nswap; ws++)
+              LAUNCH(c, mark_send_atoms_kernel, div_up(c->sw[ws].sendnum, TPB), TPB, c->sw[ws].list.as<int>(), c->sw[ws].sendnum,
+                     c->nlocal, c->send_flag.as<unsigned char>());
+          }
+          LAUNCH(c, tile_classify_kernel, div_up(g.ntiles, 4), 128, g, c->tile_runs.as<int2>(), c->tile_center.as<int4>(),
+                 c->tile_info.as<int2>(), c->tile_slots.as<int>(), c->nlocal,
+                 want_split ? c->send_flag.as<unsigned char>() : (const unsigned char*)nullptr, c->tile_split.as<int>(), c->d_scal + 16);
           CU(cudaMemcpyAsync(c->h_scal + 16, c->d_scal + 16, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
           CU(cudaStreamSynchronize(c->stream));
           c->n_interior = c->h_scal[16];
@@ -925,13 +941,22 @@ template <class T> struct Impl {
       Q.cutforcesq_tab = P.cutforcesq_tab; Q.sigma6_tab = P.sigma6_tab; Q.epsilon_tab = P.epsilon_tab;
       Q.ntypes = P.ntypes; Q.e_scale = P.e_scale; Q.v_scale = P.v_scale;
       MM(smem_optin(c, force_lj_dealt_kernel<T, EV, UNI, INTEG>));
+      GhostImages<T> GI;
+      memset(&GI, 0, sizeof GI);
+      if (INTEG && part == 0 && c->images_ready && c->ghosts_resolved && c->fuse_ghosts && c->fuse_halo) {
+        GI.start = c->img_start.as<int>();
+        GI.list = c->img_list.as<int2>();
+        GI.prd[0] = (T)c->prd[0]; GI.prd[1] = (T)c->prd[1]; GI.prd[2] = (T)c->prd[2];
+        GI.nlocal = c->nlocal;
+      }
       const int* list = c->tile_split.as<int>() + (part == 0 ? 2 * g.ntiles : (part == 2 ? g.ntiles : 0));
       const int grid = part == 0 ? c->n_active : (part == 1 ? c->n_interior : c->n_boundary);
       LAUNCH_ON(c, part == 1 ? c->stream2 : c->stream, (force_lj_dealt_kernel<T, EV, UNI, INTEG>), grid, TILE_THREADS,
                 qwin_smem_bytes<T>(g.hcap, !UNI, scap), c->x.as<V>(), c->f.as<V>(), g, c->tile_runs.as<int2>(),
                 c->tile_center.as<int4>(), c->tile_info.as<int2>(), mirror(c, c->xs_cur), c->xs_types.as<unsigned char>(),
                 c->trowsq.as<unsigned long long>(), c->tnum.as<int2>(), c->tcapq, c->nlocal, scap, Q, VP,
-                mirror(c, c->xs_cur ^ 1), c->d_ev, list, c->kernel_profile ? c->d_prof : (unsigned long long*)nullptr);
+                mirror(c, c->xs_cur ^ 1), c->d_ev, list, GI, c->kernel_profile ? c->d_prof : (unsigned long long*)nullptr);
+      if (INTEG && GI.start) { c->ghosts_fresh = true; c->fused_halo_steps++; }
       // the epilogue wrote the local atoms' new positions into the other mirror buffer (ghosts follow with the next
       // forward halo, as in x_alt); with a split launch the buffers flip once, after the second part
       if (INTEG && part != 1) c->xs_cur ^= 1;
@@ -971,8 +996,8 @@ template <class T> struct Impl {
     return MMD_OK;
   }
   // One fused step of several ranks with the forward halo hidden behind the interior tiles:
-  //   stream2: [boundary(n-1) done]                    interior(n)
-  //   stream : [interior(n-1) done]  forward halo(n)   boundary(n)
+  //   stream2: [boundary(n-1) done]  interior(n)
+  //   stream :  forward halo(n)      [interior(n-1) done]  boundary(n)
   // Both parts read the position buffers of step n and write those of step n+1; the halo writes ghost slots only, which
   // no interior window contains.  (No energies on this path: thermo steps run the single launch.)
   static int lj_split_step(mmd_ctx* c, int half, double dt, double dtforce, double mass) {
@@ -985,14 +1010,16 @@ template <class T> struct Impl {
       c->split_active = true;
       c->ev_int_valid = false;
     }
-    CU(cudaStreamWaitEvent(c->stream2, c->ev_bnd, 0));
-    if (c->lj_uniform) MM((lj_tile_launch<0, 1, 1>(c, half, VP, 1))); else MM((lj_tile_launch<0, 0, 1>(c, half, VP, 1)));
-    const bool had_int = c->ev_int_valid;
-    if (had_int) CU(cudaStreamWaitEvent(c->stream, c->ev_int, 0));
-    CU(cudaEventRecord(c->ev_int, c->stream2));
-    c->ev_int_valid = true;
+    // the halo reads send-list atoms only, all of them owned by boundary tiles (tile_classify_kernel): it follows the
+    // previous boundary kernel in stream order and may overlap the tail of the previous interior kernel
     MM(communicate(c, false));
     MM(phase_mark(c, MMD_PHASE_COMM));
+    CU(cudaStreamWaitEvent(c->stream2, c->ev_bnd, 0));
+    if (c->lj_uniform) MM((lj_tile_launch<0, 1, 1>(c, half, VP, 1))); else MM((lj_tile_launch<0, 0, 1>(c, half, VP, 1)));
+    // boundary windows hold atoms the previous interior kernel moved
+    if (c->ev_int_valid) CU(cudaStreamWaitEvent(c->stream, c->ev_int, 0));
+    CU(cudaEventRecord(c->ev_int, c->stream2));
+    c->ev_int_valid = true;
     if (c->lj_uniform) MM((lj_tile_launch<0, 1, 1>(c, half, VP, 2))); else MM((lj_tile_launch<0, 0, 1>(c, half, VP, 2)));
     CU(cudaEventRecord(c->ev_bnd, c->stream));
     std::swap(c->x, c->x_alt);
@@ -1505,6 +1532,8 @@ template <class T> struct Impl {
     c->neigh_rows = -1;  // lists are stale until the next build
     // single rank: resolve every ghost to its local source so that the per-step forward halo is one launch
     c->ghosts_resolved = false;
+    c->images_ready = false;
+    c->ghosts_fresh = false;
     {
       bool all_self = c->fuse_halo && c->nghost > 0;
       for (int ws = 0; ws < c->swaps.nswap; ws++) all_self = all_self && is_self(c, ws);
@@ -1521,6 +1550,25 @@ template <class T> struct Impl {
                  any ? c->swaps.pbc_flagz[ws] : 0, c->ghost_src.as<int>(), c->ghost_shift.as<int>());
         }
         c->ghosts_resolved = true;
+        c->images_ready = false;
+        if (c->fuse_ghosts && c->nlocal > 0) {
+          const int n1 = c->nlocal + 1;
+          MM(c->img_start.reserve((size_t)(n1 + 1) * sizeof(int), c->stream, 0, 1.2));
+          MM(c->img_cursor.reserve((size_t)(n1 + 1) * sizeof(int), c->stream, 0, 1.2));
+          MM(c->img_list.reserve((size_t)c->nghost * sizeof(int2), c->stream, 0, 1.3));
+          CU(cudaMemsetAsync(c->img_cursor.p, 0, (size_t)(n1 + 1) * sizeof(int), c->stream));
+          LAUNCH(c, ghost_image_count_kernel, div_up(c->nghost, TPB), TPB, c->ghost_src.as<int>(), c->nghost, c->img_cursor.as<int>());
+          // exclusive scan of the counts (start[nlocal] = nghost)
+          const int ntl = std::max(1, div_up(n1, SCAN_TILE));
+          MM(c->tile_sums.reserve((size_t)ntl * sizeof(int), c->stream));
+          LAUNCH(c, scan_tile_sums_kernel, ntl, SCAN_THREADS, c->img_cursor.as<int>(), n1, c->tile_sums.as<int>(), (int*)nullptr);
+          LAUNCH(c, scan_spine_kernel, 1, 1024, c->tile_sums.as<int>(), ntl, c->img_start.as<int>() + n1, 0);
+          LAUNCH(c, scan_apply_kernel, ntl, SCAN_THREADS, c->img_cursor.as<int>(), n1, c->tile_sums.as<int>(), c->img_start.as<int>());
+          CU(cudaMemsetAsync(c->img_cursor.p, 0, (size_t)(n1 + 1) * sizeof(int), c->stream));
+          LAUNCH(c, ghost_image_fill_kernel, div_up(c->nghost, TPB), TPB, c->ghost_src.as<int>(), c->ghost_shift.as<int>(), c->nghost,
+                 c->img_start.as<int>(), c->img_cursor.as<int>(), c->img_list.as<int2>());
+          c->images_ready = true;
+        }
       }
     }
     // the second position buffer (Atom::sort scratch, target of the fused force+Verlet kernel) gets the ghost records
@@ -1558,9 +1606,12 @@ template <class T> struct Impl {
       }
       MM(split_join(c));
       if ((n + 1) % p->neigh_every) {
-        MM(communicate(c, false));
+        // (the fused force kernel of the previous step may have written this step's ghosts already)
+        if (!c->ghosts_fresh) MM(communicate(c, false));
+        c->ghosts_fresh = false;
         MM(phase_mark(c, MMD_PHASE_COMM));
       } else {
+        c->ghosts_fresh = false;
         MM(exchange(c));
         if (n + 1 >= next_sort) {
           MM(sort(c));
@@ -1603,6 +1654,7 @@ template <class T> struct Impl {
       }
     }
     MM(split_join(c));
+    c->ghosts_fresh = false;
     if (elapsed_ms) {
       CU(cudaEventRecord(c->ev1, c->stream));
       CU(cudaEventSynchronize(c->ev1));
@@ -1838,7 +1890,7 @@ int mmd_ctx_destroy(mmd_ctx* c) {
                     &c->eam_rho_der, &c->eam_z2_val, &c->eam_z2_der, &c->eam_frho_val, &c->eam_frho_der, &c->eam_cut,
                     &c->rho, &c->fp, &c->border_tiles, &c->sendbuf, &c->recvbuf, &c->exch_flag, &c->exch_pos,
                     &c->exch_holes, &c->ghost_src, &c->ghost_shift, &c->sruns, &c->tile_runs, &c->tile_center, &c->tile_info, &c->tile_slots, &c->tile_oslot, &c->trows,
-                    &c->tnum, &c->trowsq, &c->xs_rec[0], &c->xs_rec[1], &c->xs_z[0], &c->xs_z[1], &c->slot_of, &c->xs_types, &c->eam_blob1, &c->eam_blob2, &c->fp_s, &c->tile_split};
+                    &c->tnum, &c->trowsq, &c->xs_rec[0], &c->xs_rec[1], &c->xs_z[0], &c->xs_z[1], &c->slot_of, &c->xs_types, &c->eam_blob1, &c->eam_blob2, &c->fp_s, &c->tile_split, &c->send_flag, &c->img_start, &c->img_cursor, &c->img_list};
   for (DevBuf* b : bufs) b->release();
   for (int w = 0; w < MMD_MAX_SWAPS; w++) c->sw[w].list.release();
   for (int r = 0; r < (int)c->peer_win.size(); r++)
@@ -2317,6 +2369,7 @@ int mmd_query_int(mmd_ctx* c, const char* key, long long* value) {
   else if (k == "list_dealt") *value = c->list_tile && c->list_dealt;
   else if (k == "tile_dealt_capacity") *value = c->tcapq;
   else if (k == "split_steps") *value = c->split_steps;
+  else if (k == "fused_halo_steps") *value = c->fused_halo_steps;
   else if (k == "stage_clocks" || k == "cta_clocks" || k == "cta_count") {
     unsigned long long h[4] = {0, 0, 0, 0};
     if (c->d_prof) {
@@ -2355,6 +2408,8 @@ int mmd_set_option(mmd_ctx* c, const char* key, long long value) {
     if (!c->fuse_halo) c->ghosts_resolved = false;
   } else if (k == "tile_dealt") {  // 1: the LJ force kernel walks bank-dealt rows (quarter warp per atom); 0: one lane pair per row
     c->tile_dealt = value != 0;     // takes effect at the next neighbor build
+  } else if (k == "fuse_ghosts") {  // one rank: the fused force kernel also writes the periodic images (no halo launch)
+    c->fuse_ghosts = value != 0;
   } else if (k == "kernel_profile") {
     if (value && !c->d_prof) {
       if (cudaMalloc(&c->d_prof, 4 * sizeof(unsigned long long)) != cudaSuccess) return set_err(MMD_ERR_CUDA, "kernel_profile: cudaMalloc");

@@ -324,7 +324,7 @@ force_lj_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Ti
                       const unsigned char* __restrict__ types_s, const unsigned long long* __restrict__ rowsq,
                       const int2* __restrict__ row_atom, int tcapq, int nlocal, int scap, LJDealtParams<T> P,
                       VerletParams<T> VP, XsMirror<T> xs_out, double* __restrict__ ev_out,
-                      const int* __restrict__ tile_list /* nullptr: every tile, blockIdx.x = tile */,
+                      const int* __restrict__ tile_list /* tiles that own local atoms */, GhostImages<T> GI,
                       unsigned long long* __restrict__ prof /* {staging clocks, CTA clocks, CTAs}: -DMMD_KERNEL_PROFILE builds only */) {
   extern __shared__ __align__(16) unsigned char tile_smem_raw[];
   // tile_list holds tiles that own local atoms only (tile_classify_kernel): no CTA exits early, and nothing has to
@@ -501,6 +501,20 @@ force_lj_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Ti
       VP.v[id] = vi;
       VP.x_out[id] = xo;
       xs_out.put_slot(S.pc[ac >> 16].w + a, xo);
+      if (GI.start) {  // the atom's periodic images: the forward halo of the next step, done here
+        const int ib = __ldg(GI.start + id), ie = __ldg(GI.start + id + 1);
+        for (int k = ib; k < ie; k++) {
+          const int2 im = __ldg(GI.list + k);
+          const int sx = (im.y & 3) - 1, sy = ((im.y >> 2) & 3) - 1, sz = ((im.y >> 4) & 3) - 1;
+          Vec4<T> pg = xo;
+          if (sx) pg.x = pg.x + sx * GI.prd[0];
+          if (sy) pg.y = pg.y + sy * GI.prd[1];
+          if (sz) pg.z = pg.z + sz * GI.prd[2];
+          const int ga = GI.nlocal + im.x;
+          VP.x_out[ga] = pg;
+          xs_out.put_atom(ga, pg);
+        }
+      }
     } else {
       Vec4<T> out;
       out.x = fxa; out.y = fya; out.z = fza; out.w = (T)0;
@@ -534,9 +548,12 @@ force_lj_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Ti
 // window's slots; lists[0 .. counts[0]) receives the interior tiles, lists[ntiles .. ntiles + counts[1]) the others,
 // lists[2*ntiles .. 2*ntiles + counts[2]) every tile that owns local atoms (what a single launch covers).
 // ---------------------------------------------------------------------------------------
+// send_flag (may be null): 1 for every local atom that appears in a send list.  A tile that OWNS such an atom counts as
+// boundary too, so the forward halo of step n+1 only reads positions written by the boundary kernel of step n.
 __global__ void __launch_bounds__(128)
-tile_classify_kernel(TileGeo g, const int2* __restrict__ tile_runs, const int2* __restrict__ tile_info,
-                     const int* __restrict__ slots, int nlocal, int* __restrict__ lists, int* __restrict__ counts) {
+tile_classify_kernel(TileGeo g, const int2* __restrict__ tile_runs, const int4* __restrict__ tile_center,
+                     const int2* __restrict__ tile_info, const int* __restrict__ slots, int nlocal,
+                     const unsigned char* __restrict__ send_flag, int* __restrict__ lists, int* __restrict__ counts) {
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (t >= g.ntiles) return;
@@ -552,10 +569,31 @@ tile_classify_kernel(TileGeo g, const int2* __restrict__ tile_runs, const int2* 
     for (int k = lane; k < len; k += 32) gl = gl || (__ldg(slots + r.x + k) >= nlocal);
     ghost = __any_sync(0xffffffffu, gl);
   }
+  if (!ghost && send_flag) {  // own atoms: the centre pencils' index ranges
+    for (int c = 0; c < TILE_NCENTER && !ghost; c++) {
+      const int4 ce = tile_center[(size_t)t * TILE_NCENTER + c];
+      const int2 r = tr[(c % TBY + g.sy) + (c / TBY + g.sz) * g.nry];
+      bool gl = false;
+      for (int a = ce.x + lane; a < ce.y; a += 32) {
+        const int id = __ldg(slots + r.x + (a - r.y));
+        gl = gl || (id < nlocal && send_flag[id] != 0);
+      }
+      ghost = __any_sync(0xffffffffu, gl);
+    }
+  }
   if (lane == 0) {
     const int k = atomicAdd(counts + (ghost ? 1 : 0), 1);
     lists[(ghost ? g.ntiles : 0) + k] = t;
     lists[2 * g.ntiles + atomicAdd(counts + 2, 1)] = t;
+  }
+}
+
+// send_flag[list[k]] = 1 for the local atoms of one send list
+__global__ void mark_send_atoms_kernel(const int* __restrict__ list, int count, int nlocal, unsigned char* __restrict__ send_flag) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < count) {
+    const int i = list[k];
+    if (i < nlocal) send_flag[i] = 1;
   }
 }
 

@@ -56,4 +56,29 @@ __global__ void xs_refresh_kernel(const Vec4<T>* __restrict__ x, int first, int 
   M.put_atom(first + k, x[first + k]);
 }
 
+// ---------------------------------------------------------------------------------------
+// Ghost images (single rank, every swap a self swap): ghost g is a copy of local atom src[g] shifted by whole box
+// lengths (ghost_resolve_kernel).  Inverted into a CSR list per local atom, the Verlet epilogue of the force kernel
+// writes an atom's ghost copies together with its new position -- the per-step forward halo
+// (Comm::communicate, ref/comm.cpp:276-317) needs no launch of its own.  Same arithmetic as
+// halo_forward_resolved_kernel (x + s * prd per shifted coordinate): bit-identical ghosts.
+// ---------------------------------------------------------------------------------------
+template <class T> struct GhostImages {
+  const int* start;   // [nlocal + 1]; nullptr: no images to write
+  const int2* list;   // {ghost index (0-based behind the local atoms), packed shift: 2 bits per axis holding s + 1}
+  T prd[3];
+  int nlocal;
+};
+__global__ void ghost_image_count_kernel(const int* __restrict__ src, int nghost, int* __restrict__ count) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < nghost) atomicAdd(count + src[g], 1);
+}
+__global__ void ghost_image_fill_kernel(const int* __restrict__ src, const int* __restrict__ shift, int nghost,
+                                        const int* __restrict__ start, int* __restrict__ cursor, int2* __restrict__ list) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nghost) return;
+  const int s = src[g];
+  list[start[s] + atomicAdd(cursor + s, 1)] = make_int2(g, shift[g]);
+}
+
 }  // namespace mmd

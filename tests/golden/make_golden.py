@@ -13,6 +13,8 @@ NPZ files this script writes.
                         funcfl text file for runs (17 significant digits => identical doubles).
 
 usage: python tests/golden/make_golden.py [--big]     (--big adds -s 80 / EAM -s 64; minutes)
+       python tests/golden/make_golden.py --weak       (only ADDS the weak-scaling boxes of bench.py --gpus 2/4/8:
+                                                        80x80x160, 80x160x160, 160^3 cells; ~10 minutes, ~10 GB)
 """
 import json
 import os
@@ -62,7 +64,7 @@ def shipped_logs():
     return logs
 
 
-def reference_runs(big):
+def reference_runs(big, weak_only=False):
     cases = {}
 
     def add(name, cfg, precision="f64", threads=1):
@@ -77,6 +79,11 @@ def reference_runs(big):
         }
         print(name, r.steps[-1], r.T[-1], r.U[-1], r.P[-1], r.nghost, r.neighs, flush=True)
 
+    if weak_only:  # 80^3 cells per GPU on 2 / 4 / 8 ranks
+        add("lj_80x80x160_half", Config(nx=80, ny=80, nz=160), threads=8)
+        add("lj_80x160x160_half", Config(nx=80, ny=160, nz=160), threads=8)
+        add("lj_s160_half", Config(nx=160, ny=160, nz=160), threads=8)
+        return cases
     for force in ("lj", "eam"):
         for half, gn in ((1, 1), (1, 0), (0, 0)):
             add(f"{force}_s8_half{half}_gn{gn}", Config(nx=8, ny=8, nz=8, force=force, halfneigh=half, ghost_newton=gn,
@@ -109,6 +116,13 @@ def funcfl_table():
 
 def main():
     big = "--big" in sys.argv
+    if "--weak" in sys.argv:
+        path = os.path.join(HERE, "reference_runs.json")
+        runs = json.load(open(path))
+        runs.update(reference_runs(False, weak_only=True))
+        with open(path, "w") as fh:
+            json.dump(runs, fh, indent=0)
+        return
     with open(os.path.join(HERE, "reference_logs.json"), "w") as fh:
         json.dump(shipped_logs(), fh, indent=0)
     np.savez_compressed(os.path.join(HERE, "cu_u6_funcfl.npz"), **funcfl_table())

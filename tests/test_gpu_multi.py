@@ -37,6 +37,10 @@ CASES = [
     (4, ["--cells", 12, 24, 24]),
     (8, ["--cells", 24, 24, 24]),
     (8, ["--cells", 20, 20, 20, "--force", "eam", "--half_neigh", 0]),
+    # the boxes bench.py --gpus 2/4/8 runs (80^3 cells per GPU), against the unmodified reference binary's T/U/P at step 100
+    (2, ["--cells", 80, 80, 160, "--golden", "lj_80x80x160_half", "--tol", 1e-7]),
+    (4, ["--cells", 80, 160, 160, "--golden", "lj_80x160x160_half", "--tol", 1e-7]),
+    (8, ["--cells", 160, 160, 160, "--golden", "lj_s160_half", "--tol", 1e-7]),
 ]
 
 

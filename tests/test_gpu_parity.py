@@ -457,7 +457,8 @@ def test_fused_paths_reproduce_the_unfused_ones(prec):
     assert halo[3] < base[3]
     # Verlet halves in one kernel / in the force kernel's epilogue: same operations in the same order
     for opts in (dict(fuse_halo=1, fuse_force=0, fuse_integrate=1), dict(fuse_halo=1, fuse_force=1, fuse_integrate=1),
-                 dict(fuse_halo=1, fuse_force=1, fuse_integrate=1, tile_dealt=0)):
+                 dict(fuse_halo=1, fuse_force=1, fuse_integrate=1, tile_dealt=0),
+                 dict(fuse_halo=1, fuse_force=1, fuse_integrate=1, fuse_ghosts=1)):
         got = _run_with(opts, prec)
         tol = 1e-12 if prec == "f64" else 5e-5
         assert_close(got[1], base[1], tol, f"x {opts}")
