@@ -16,11 +16,19 @@ e2e     : the same neighbor cycle through the C ABI with HOST buffers: every ste
           from pinned host memory (mmd_atom_upload), rebuilds ghosts + lists + forces as the
           reference's main() does after setup (ref/ljs.cpp:445-459), runs the 20 MD steps, and
           downloads x, v and the thermo sums; wall clock with synchronisation on both sides.
-roofline: the force kernel (the dominant launch) -- algorithmic bytes per launch (SURVEY.md 8d row
-          formulas with the neighbor count measured in this run) / its CUDA-event duration inside the
-          timed region, against MEASURED_PEAKS.json's HBM copy bandwidth.
+roofline: the force launch of one MD step (the dominant kernel; with tile lists it also performs the
+          two velocity-Verlet halves) -- algorithmic bytes per launch (SURVEY.md 8d row formulas with
+          the neighbor count measured in this run) / its CUDA-event duration inside the timed region,
+          against MEASURED_PEAKS.json's HBM copy bandwidth.  `fp64_frac`: pair evaluations per second
+          against the measured FP64 pair rate (profiles/r2_fp64_peak.json, tools/microbench/
+          fp64_fma_bench.cu).  `traffic`: DRAM bytes per launch from the committed ncu capture of THIS
+          kernel on THIS workload (profiles/traffic.json names kernel, atoms and source) or null.
+other_configs (N=1): BASELINE.json configs[2] (`-s 80` full list FP32) and configs[3] (EAM `-s 64`
+          full list FP64), a few cycles each, each with its own roofline / e2e / cpu_baseline.
 cpu_baseline / --impl reference: the UNMODIFIED reference binary (oracle/_ref, built by
-          oracle/build_ref.sh) on this box's host cores, OpenMP over all of them, bounded sample.
+          oracle/build_ref.sh) on this box's host cores, OpenMP over all of them, bounded sample;
+          the reference arm runs --warmup + --steps cycles in one process (or fewer if they would
+          not end within ~150 s, and then says so in `steps`).
 """
 from __future__ import annotations
 
