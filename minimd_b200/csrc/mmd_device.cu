@@ -1471,37 +1471,35 @@ template <class T> struct Impl {
         const T lo1 = (T)c->swaps.slablo[w + 1], hi1 = (T)c->swaps.slabhi[w + 1];
         LAUNCH(c, border_count_kernel<T>, ntiles, BORDER_THREADS, c->x.as<V>(), nfirst, nlast, dim, lo0, hi0, lo1, hi1, t0, t1);
         LAUNCH(c, scan_spine_kernel, 2, 1024, t0, ntiles, c->d_scal + 3, ntiles);
-        CU(cudaMemcpyAsync(c->h_scal + 3, c->d_scal + 3, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        const bool self0 = is_self(c, w), self1 = is_self(c, w + 1);
+        int* d_cnt = c->d_scal + 6;  // [8],[9] counts received from the partners of the two swaps
+        if (!self0 || !self1) {
+#ifdef MMD_WITH_NCCL
+          // the send counts travel straight from the device scalars the scan wrote (ref/comm.cpp:822-824): one host
+          // round trip below reads them together with the counts received
+          if (!c->nccl) return set_err(MMD_ERR_STATE, "remote swap requested but mmd_comm_nccl_init was not called");
+          CU(cudaMemsetAsync(d_cnt + 2, 0, 2 * sizeof(int), c->stream));
+          NC(ncclGroupStart());
+          if (!self0) { NC(ncclSend(c->d_scal + 3, 1, ncclInt, c->swaps.sendproc[w], c->nccl, c->stream));
+                        NC(ncclRecv(d_cnt + 2, 1, ncclInt, c->swaps.recvproc[w], c->nccl, c->stream)); }
+          if (!self1) { NC(ncclSend(c->d_scal + 4, 1, ncclInt, c->swaps.sendproc[w + 1], c->nccl, c->stream));
+                        NC(ncclRecv(d_cnt + 3, 1, ncclInt, c->swaps.recvproc[w + 1], c->nccl, c->stream)); }
+          NC(ncclGroupEnd());
+#else
+          return set_err(MMD_ERR_STATE, "remote swap but library built without NCCL");
+#endif
+        }
+        CU(cudaMemcpyAsync(c->h_scal + 3, c->d_scal + 3, 7 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));  // [3..9]
         CU(cudaStreamSynchronize(c->stream));
         const int ns0 = c->h_scal[3], ns1 = c->h_scal[4];
         MM(c->sw[w].list.reserve((size_t)std::max(ns0, 1) * sizeof(int), c->stream, 0, 1.5));
         MM(c->sw[w + 1].list.reserve((size_t)std::max(ns1, 1) * sizeof(int), c->stream, 0, 1.5));
-        const bool self0 = is_self(c, w), self1 = is_self(c, w + 1);
-        int nr0 = ns0, nr1 = ns1;
+        const int nr0 = self0 ? ns0 : c->h_scal[8], nr1 = self1 ? ns1 : c->h_scal[9];
         T *b0 = nullptr, *b1 = nullptr;
         if (!self0 || !self1) {
-#ifdef MMD_WITH_NCCL
           MM(c->sendbuf.reserve((size_t)4 * (ns0 + ns1) * sizeof(T), c->stream, 0, 1.5));
           b0 = c->sendbuf.as<T>();
           b1 = b0 + (size_t)4 * ns0;
-          // counts first (ref/comm.cpp:822-824); ints travel through the pinned/host path via NCCL int buffers
-          int* d_cnt = c->d_scal + 6;  // [6],[7] send counts, [8],[9] recv counts
-          c->h_scal[6] = ns0; c->h_scal[7] = ns1;
-          CU(cudaMemcpyAsync(d_cnt, c->h_scal + 6, 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-          if (!c->nccl) return set_err(MMD_ERR_STATE, "remote swap requested but mmd_comm_nccl_init was not called");
-          NC(ncclGroupStart());
-          if (!self0) { NC(ncclSend(d_cnt + 0, 1, ncclInt, c->swaps.sendproc[w], c->nccl, c->stream));
-                        NC(ncclRecv(d_cnt + 2, 1, ncclInt, c->swaps.recvproc[w], c->nccl, c->stream)); }
-          if (!self1) { NC(ncclSend(d_cnt + 1, 1, ncclInt, c->swaps.sendproc[w + 1], c->nccl, c->stream));
-                        NC(ncclRecv(d_cnt + 3, 1, ncclInt, c->swaps.recvproc[w + 1], c->nccl, c->stream)); }
-          NC(ncclGroupEnd());
-          CU(cudaMemcpyAsync(c->h_scal + 8, d_cnt + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-          CU(cudaStreamSynchronize(c->stream));
-          if (!self0) nr0 = c->h_scal[8];
-          if (!self1) nr1 = c->h_scal[9];
-#else
-          return set_err(MMD_ERR_STATE, "remote swap but library built without NCCL");
-#endif
         }
         const int first0 = c->nlocal + c->nghost, first1 = first0 + nr0;
         MM(reserve_atoms(c, first1 + nr1));
@@ -1666,12 +1664,14 @@ template <class T> struct Impl {
   }
 
   // exclusive scan of flags[0,n) into pos[0,n] (pos[n] = total); the total also lands in h_scal[5]
+  // total == nullptr: no host round trip, the total stays on the device in pos[n]
   static int scan_flags(mmd_ctx* c, const int* flags, int n, int* pos, int* total) {
     const int ntiles = std::max(1, div_up(n, SCAN_TILE));
     MM(c->tile_sums.reserve((size_t)ntiles * sizeof(int), c->stream));
     LAUNCH(c, scan_tile_sums_kernel, ntiles, SCAN_THREADS, flags, n, c->tile_sums.as<int>(), (int*)nullptr);
     LAUNCH(c, scan_spine_kernel, 1, 1024, c->tile_sums.as<int>(), ntiles, pos + n, 0);
     LAUNCH(c, scan_apply_kernel, ntiles, SCAN_THREADS, flags, n, c->tile_sums.as<int>(), pos);
+    if (!total) return MMD_OK;
     CU(cudaMemcpyAsync(c->h_scal + 5, pos + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     *total = c->h_scal[5];
@@ -1694,11 +1694,26 @@ template <class T> struct Impl {
       const bool both = c->swaps.procgrid[d] > 2;
       MM(c->exch_flag.reserve((size_t)(n + 2) * sizeof(int), c->stream, 0, 1.2));
       MM(c->exch_pos.reserve((size_t)(n + 2) * sizeof(int), c->stream, 0, 1.2));
-      int nsend = 0;
+      // my count stays on the device (exch_pos[n], written by the scan) and travels from there; ONE host round trip
+      // then reads it together with the counts the neighbours sent (ref/comm.cpp:521-530)
+      int* d_cnt = c->d_scal + 6;  // [6] my count, [8] from upper, [9] from lower
+      CU(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(int), c->stream));
       if (n > 0) {
         LAUNCH(c, exch_flag_kernel<T>, div_up(n, TPB), TPB, c->x.as<V>(), n, d, lo, hi, c->exch_flag.as<int>());
-        MM(scan_flags(c, c->exch_flag.as<int>(), n, c->exch_pos.as<int>(), &nsend));
+        MM(scan_flags(c, c->exch_flag.as<int>(), n, c->exch_pos.as<int>(), nullptr));
+        CU(cudaMemcpyAsync(d_cnt, c->exch_pos.as<int>() + n, sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
       }
+      NC(ncclGroupStart());
+      NC(ncclSend(d_cnt, 1, ncclInt, lower, c->nccl, c->stream));
+      NC(ncclRecv(d_cnt + 2, 1, ncclInt, upper, c->nccl, c->stream));
+      if (both) {
+        NC(ncclSend(d_cnt, 1, ncclInt, upper, c->nccl, c->stream));
+        NC(ncclRecv(d_cnt + 3, 1, ncclInt, lower, c->nccl, c->stream));
+      }
+      NC(ncclGroupEnd());
+      CU(cudaMemcpyAsync(c->h_scal + 6, d_cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      const int nsend = c->h_scal[6];
       const int nkeep = n - nsend;
       if (nsend > 0) {
         MM(c->sendbuf.reserve((size_t)7 * nsend * sizeof(T), c->stream, 0, 1.5));
@@ -1711,22 +1726,6 @@ template <class T> struct Impl {
       }
       c->nlocal = nkeep;
       c->exch_sent += nsend;
-      // counts (ref/comm.cpp:521-530), then payloads (:535-544)
-      int* d_cnt = c->d_scal + 6;  // [6] my count, [8] from upper, [9] from lower
-      c->h_scal[6] = nsend;
-      c->h_scal[8] = c->h_scal[9] = 0;
-      CU(cudaMemcpyAsync(d_cnt, c->h_scal + 6, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-      CU(cudaMemsetAsync(d_cnt + 2, 0, 2 * sizeof(int), c->stream));
-      NC(ncclGroupStart());
-      NC(ncclSend(d_cnt, 1, ncclInt, lower, c->nccl, c->stream));
-      NC(ncclRecv(d_cnt + 2, 1, ncclInt, upper, c->nccl, c->stream));
-      if (both) {
-        NC(ncclSend(d_cnt, 1, ncclInt, upper, c->nccl, c->stream));
-        NC(ncclRecv(d_cnt + 3, 1, ncclInt, lower, c->nccl, c->stream));
-      }
-      NC(ncclGroupEnd());
-      CU(cudaMemcpyAsync(c->h_scal + 8, d_cnt + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-      CU(cudaStreamSynchronize(c->stream));
       const int nrecv1 = c->h_scal[8], nrecv2 = both ? c->h_scal[9] : 0;
       const int nrecv = nrecv1 + nrecv2;
       MM(c->recvbuf.reserve((size_t)7 * std::max(nrecv, 1) * sizeof(T), c->stream, 0, 1.5));
