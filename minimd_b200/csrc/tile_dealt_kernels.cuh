@@ -308,6 +308,30 @@ __device__ __forceinline__ void lj_pair(const QWin<T>& S, const LJDealtParams<T>
   }
 }
 
+// FP32, uniform parameters: TWO neighbors at a time on Blackwell's packed FP32 pipe (FFMA2 / FMUL2: one instruction,
+// two IEEE FP32 results).  The FP32 launch is issue-bound, and the pair body is 17 FP32 instructions: packing two
+// neighbors into every arithmetic instruction removes about a quarter of the kernel's instructions.  f2 = (fxA, fxB)
+// etc. are pairs of partial sums, added up once per atom.  EV = 0 only (thermo steps take the scalar path).
+__device__ __forceinline__ void lj_pair2_f32(const QWin<float>& S, const LJDealtParams<float>& P, int ljA, int ljB, float2 xi2,
+                                             float2 yi2, float2 zi2, float2& fx2, float2& fy2, float2& fz2) {
+  const QRec<float> a = S.rec[ljA], b = S.rec[ljB];
+  const float2 m1 = make_float2(-1.0f, -1.0f);
+  const float2 dx = __ffma2_rn(make_float2(a.x, b.x), m1, xi2);
+  const float2 dy = __ffma2_rn(make_float2(a.y, b.y), m1, yi2);
+  const float2 dz = __ffma2_rn(make_float2(a.z, b.z), m1, zi2);
+  const float2 rsq = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+  const float2 a1 = make_float2(__frcp_rn(rsq.x), __frcp_rn(rsq.y));
+  const float2 a2 = __fmul2_rn(a1, a1);
+  const float2 a3 = __fmul2_rn(a2, a1);
+  const float2 t = __ffma2_rn(a3, make_float2(P.sigma6, P.sigma6), make_float2(-0.5f, -0.5f));
+  float2 force = __fmul2_rn(__fmul2_rn(__fmul2_rn(a2, a2), t), make_float2(P.k48, P.k48));
+  force.x = rsq.x < P.cutforcesq ? force.x : 0.0f;
+  force.y = rsq.y < P.cutforcesq ? force.y : 0.0f;
+  fx2 = __ffma2_rn(dx, force, fx2);
+  fy2 = __ffma2_rn(dy, force, fy2);
+  fz2 = __ffma2_rn(dz, force, fz2);
+}
+
 // INTEG = 1: the velocity-Verlet halves that follow the force ride in the epilogue (see VerletParams, tile_kernels.cuh):
 // new positions go to x_out[] AND to the other buffer of the slot-ordered mirror (xs_out), which the next launch stages.
 //
@@ -445,22 +469,40 @@ force_lj_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Ti
     if (UNIFORM) S.get(a, xi, yi, zi); else S.get(a, xi, yi, zi, ti);
     T fx = 0, fy = 0, fz = 0;
     const int nfull = gmax >> 2;
+    constexpr bool PACKED = sizeof(T) == 4 && UNIFORM && !EV;  // FP32: two neighbors per packed instruction
+    float2 fx2 = make_float2(0.f, 0.f), fy2 = fx2, fz2 = fx2;
+    float2 xi2, yi2, zi2;
+    if constexpr (PACKED) { xi2 = make_float2(xi, xi); yi2 = make_float2(yi, yi); zi2 = make_float2(zi, zi); }
     for (int b = 0; b < nfull; b++) {
       const unsigned long long cur = w0;
       w0 = w1;
       w1 = sent4;
       if (b + 2 < nwords) w1 = ldg_rowq(rowq + (size_t)(b + 2) * QL);
-      // four independent pair evaluations in flight: the FP64 dependency chains overlap
+      if constexpr (PACKED) {
+        lj_pair2_f32(S, P, (int)(cur & 0x7fffull), (int)((cur >> 16) & 0x7fffull), xi2, yi2, zi2, fx2, fy2, fz2);
+        lj_pair2_f32(S, P, (int)((cur >> 32) & 0x7fffull), (int)((cur >> 48) & 0x7fffull), xi2, yi2, zi2, fx2, fy2, fz2);
+      } else {
+        // four independent pair evaluations in flight: the FP64 dependency chains overlap
 #pragma unroll
-      for (int e = 0; e < QB; e++)
-        lj_pair<T, EV, UNIFORM>(S, P, (int)((cur >> (16 * e)) & 0x7fffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
+        for (int e = 0; e < QB; e++)
+          lj_pair<T, EV, UNIFORM>(S, P, (int)((cur >> (16 * e)) & 0x7fffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
+      }
     }
     if (gmax & 2) {
-      lj_pair<T, EV, UNIFORM>(S, P, (int)(w0 & 0x7fffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
-      lj_pair<T, EV, UNIFORM>(S, P, (int)((w0 >> 16) & 0x7fffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
+      if constexpr (PACKED) {
+        lj_pair2_f32(S, P, (int)(w0 & 0x7fffull), (int)((w0 >> 16) & 0x7fffull), xi2, yi2, zi2, fx2, fy2, fz2);
+      } else {
+        lj_pair<T, EV, UNIFORM>(S, P, (int)(w0 & 0x7fffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
+        lj_pair<T, EV, UNIFORM>(S, P, (int)((w0 >> 16) & 0x7fffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
+      }
     }
     if (gmax & 1)
       lj_pair<T, EV, UNIFORM>(S, P, (int)((w0 >> ((gmax & 2) * 16)) & 0x7fffull), xi, yi, zi, ti, fx, fy, fz, eng, vir);
+    if constexpr (PACKED) {
+      fx += fx2.x + fx2.y;
+      fy += fy2.x + fy2.y;
+      fz += fz2.x + fz2.y;
+    }
     fx = group_sum<QL>(fx);
     fy = group_sum<QL>(fy);
     fz = group_sum<QL>(fz);
