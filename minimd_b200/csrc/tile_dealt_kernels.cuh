@@ -34,30 +34,69 @@ constexpr int QBLK = QL * QB;    // entries per row block (64 bytes)
 
 __host__ __device__ inline int dealt_capacity(int longest_row) { return ((longest_row > 1 ? longest_row : 1) + QBLK - 1) / QBLK * QBLK; }
 
+// ---- asynchronous staging primitives (sm_90+): mbarrier + bulk copy (TMA engine, SASS UBLKCP) + cp.async (LDGSTS) ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// global -> shared bulk copy, completion counted in bytes on the mbarrier; dst, src and bytes are multiples of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---------------------------------------------------------------------------------------
-// rows in candidate order (neigh_build_*_kernel) -> bank-dealt rows.  A CTA takes 128 consecutive rows: it copies them
-// into shared memory with coalesced 16-byte loads, then ONE THREAD PER ROW counts the 8 classes and places every entry
-// at its dealt position inside a second shared-memory copy (odd word strides: the threads' accesses spread over the
-// banks), and the CTA writes the dealt rows out with 16-byte stores.  Empty slots of a lane p hold the sentinel index
-// sentinel0 + p: hcap-8 .. hcap-1 are eight far-away atoms, one per bank class, so that a sentinel read by lane p (which
-// mostly holds entries of the classes around p) rarely collides with a real entry of its group.
+// rows in candidate order (neigh_build_*_kernel) -> bank-dealt rows.  A CTA takes 128 consecutive rows: ONE bulk copy
+// (cp.async.bulk, completion on an mbarrier) brings them into shared memory while the threads prefill the sentinel
+// pattern of the output; then ONE THREAD PER ROW counts the 8 classes and places every entry at its dealt position
+// inside a second shared-memory copy, and the CTA writes the dealt rows out with 16-byte stores.  The staged rows keep
+// their global stride (tcap/2 words, a multiple of 4), so thread r starts its walk at word (r - r*stride) mod 32 of
+// its row and wraps: the threads of a warp then sit on 32 different banks.  Empty slots of a lane p hold the sentinel
+// index sentinel0 + p: hcap-8 .. hcap-1 are eight far-away atoms, one per bank class, so that a sentinel read by lane
+// p (which mostly holds entries of the classes around p) rarely collides with a real entry of its group.
 // ---------------------------------------------------------------------------------------
 constexpr int DEAL_THREADS = 128;
 constexpr int DEAL_MAXROW = 255;  // longest row the 8-bit class counters handle
 __host__ __device__ inline size_t deal_smem_bytes(int tcap, int tcapq) {
-  return (size_t)DEAL_THREADS * ((tcap / 2 + 1) + (tcapq / 2 + 1)) * 4 + DEAL_THREADS * 4;
+  return (size_t)DEAL_THREADS * ((tcap / 2) + (tcapq / 2 + 1)) * 4 + DEAL_THREADS * 4 + 16;
 }
 
 __global__ void __launch_bounds__(DEAL_THREADS)
 tile_rows_deal_kernel(const unsigned short* __restrict__ rows, const int2* __restrict__ row_atom, int nrows, int tcap,
                       int nlocal, unsigned short* __restrict__ rowsq, int tcapq, int sentinel0) {
   extern __shared__ __align__(16) unsigned char deal_smem[];
-  const int sstride = tcap / 2 + 1, dstride = tcapq / 2 + 1;  // words per row, both odd
+  const int sstride = tcap / 2, dstride = tcapq / 2 + 1;  // words per row: staged rows as in global memory, dealt rows odd
   unsigned* s_src = reinterpret_cast<unsigned*>(deal_smem);
   unsigned* s_dst = s_src + DEAL_THREADS * sstride;
   int* s_n = reinterpret_cast<int*>(s_dst + DEAL_THREADS * dstride);
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>((reinterpret_cast<size_t>(s_n + DEAL_THREADS) + 7) & ~(size_t)7);
   const int q0 = blockIdx.x * DEAL_THREADS;
   const int q = q0 + threadIdx.x;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    const unsigned bytes = (unsigned)min(DEAL_THREADS, nrows - q0) * (unsigned)tcap * 2u;  // tcap is a multiple of 8
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(s_src, rows + (size_t)q0 * tcap, bytes, bar);
+  }
   int n = 0;
   if (q < nrows) {
     const int2 ta = row_atom[q];
@@ -73,37 +112,32 @@ tile_rows_deal_kernel(const unsigned short* __restrict__ rows, const int2* __res
       d[k] = sv | (sv << 16);
     }
   }
-  __syncthreads();
-  {  // coalesced copy-in: 8 rows per step, 16 lanes x 16 bytes per row (independent steps: the loads pipeline)
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-#pragma unroll 4
-    for (int r = ty; r < DEAL_THREADS; r += DEAL_THREADS / 16) {
-      const int nr = s_n[r];
-      for (int ch = tx; ch * 8 < nr; ch += 16) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(rows + (size_t)(q0 + r) * tcap + ch * 8));
-        unsigned* d = s_src + r * sstride + ch * 4;
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-      }
-    }
-  }
-  __syncthreads();
+  __syncthreads();      // the barrier is initialised, s_n is complete
+  mbar_wait(bar, 0);    // the staged rows have landed
   if (n > 0) {
     // class counts, 8 bits each (n <= 255): classes 0-3 in c0, 4-7 in c1; two entries per shared-memory word
     const unsigned* __restrict__ srcw = s_src + threadIdx.x * sstride;
     unsigned c0 = 0u, c1 = 0u;
     const int nw2 = (n + 1) >> 1;
-    for (int k = 0; k < nw2; k++) {
-      const unsigned wd = srcw[k];
+    // first word of this thread's walk.  The dealt positions must not depend on it (row numbers are handed out to the
+    // tiles in launch order, so a row's thread index differs from run to run): entries are ranked within their class
+    // in ROW order -- the walk starts with the rank of its first word and falls back to zero when it wraps
+    const int rot = ((threadIdx.x - threadIdx.x * sstride) & 31) % nw2;
+    unsigned snap0 = 0u, snap1 = 0u;   // class counts of the words [rot, nw2)
+    for (int k = 0, kk = rot; k < nw2; k++) {
+      const unsigned wd = srcw[kk];
       const unsigned i0 = 1u << ((wd & 3u) << 3), i1 = 1u << (((wd >> 16) & 3u) << 3);
-      const bool two = 2 * k + 1 < n;
+      const bool two = 2 * kk + 1 < n;
       c0 += (wd & 4u) ? 0u : i0;
       c1 += (wd & 4u) ? i0 : 0u;
       c0 += (two && !(wd & 0x40000u)) ? i1 : 0u;
       c1 += (two && (wd & 0x40000u)) ? i1 : 0u;
+      if (kk + 1 == nw2) { kk = 0; snap0 = c0; snap1 = c1; } else kk++;
     }
     // exclusive prefix over the classes (byte k of the product = sum of the bytes below k; totals < 256)
-    unsigned p0 = c0 * 0x01010100u;
-    unsigned p1 = c1 * 0x01010100u + ((c0 * 0x01010101u) >> 24) * 0x01010101u;
+    const unsigned base0 = c0 * 0x01010100u;
+    const unsigned base1 = c1 * 0x01010100u + ((c0 * 0x01010101u) >> 24) * 0x01010101u;
+    unsigned p0 = base0 + (c0 - snap0), p1 = base1 + (c1 - snap1);   // + the class members in the words [0, rot): no byte carries
     const int G = (n + QL - 1) / QL;
     const float rG = 1.0f / (float)G;
     unsigned short* dst = reinterpret_cast<unsigned short*>(s_dst + threadIdx.x * dstride);
@@ -120,10 +154,11 @@ tile_rows_deal_kernel(const unsigned short* __restrict__ rows, const int2* __res
       const int g = t - p * G;
       dst[((g >> 2) << 5) + (p << 2) + (g & 3)] = (unsigned short)ent;   // the half-list flag (bit 15) travels along
     };
-    for (int k = 0; k < nw2; k++) {
-      const unsigned wd = srcw[k];
+    for (int k = 0, kk = rot; k < nw2; k++) {
+      const unsigned wd = srcw[kk];
       place(wd & 0xffffu);
-      if (2 * k + 1 < n) place(wd >> 16);
+      if (2 * kk + 1 < n) place(wd >> 16);
+      if (kk + 1 == nw2) { kk = 0; p0 = base0; p1 = base1; } else kk++;
     }
   }
   __syncthreads();
@@ -206,36 +241,6 @@ template <class T> __host__ __device__ inline size_t qwin_smem_bytes(int hcap, b
   return (size_t)hcap * (sizeof(T) == 8 ? 24 : 16) + TILE_NCENTER * sizeof(int4) + 16 + (size_t)scap * (3 * sizeof(T) + sizeof(int)) +
          (20 + 2 * TILE_MAXRUN + 1) * sizeof(int) + ((with_types && sizeof(T) == 8) ? (size_t)hcap : 0) + 16;
 }
-
-// ---- asynchronous staging primitives (sm_90+): mbarrier + bulk copy (TMA engine, SASS UBLKCP) + cp.async (LDGSTS) ----
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  unsigned ok;
-  do {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  } while (!ok);
-}
-// global -> shared bulk copy, completion counted in bytes on the mbarrier; dst, src and bytes are multiples of 16
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // one 64-bit row word = the entries of four consecutive groups; the L2::128B hint pulls the atom's next block too
 __device__ __forceinline__ unsigned long long ldg_rowq(const unsigned long long* p) {
