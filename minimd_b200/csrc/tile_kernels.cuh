@@ -732,6 +732,11 @@ __global__ void bin_xsort_kernel(const Vec4<T>* __restrict__ x, const int* __res
 // with one REDUX.OR + POPC.  Distance test, guard band, exact FP64 re-test, half-list flag, counters and row layout
 // are those of neigh_build_tile2_kernel; rows come out in candidate order (ascending tile-local index).
 // ---------------------------------------------------------------------------------------
+// 16-bit store to global memory (the pointer went through an opaque asm, so the compiler no longer knows its space)
+__device__ __forceinline__ void stg_u16(unsigned short* p, unsigned short v) {
+  asm volatile("st.global.u16 [%0], %1;" ::"l"(p), "h"(v) : "memory");
+}
+
 template <class T> __host__ __device__ inline size_t build3_smem_bytes(const TileGeo& g, int hcap, bool with_types) {
   return (size_t)hcap * 3 * sizeof(float) + (with_types ? (size_t)hcap : 0) + (size_t)g.nrun * (TBX + 2 * g.sx + 1) * sizeof(int) +
          (size_t)TB2_WARPS * 32 * sizeof(int4) + (2 * TILE_MAXRUN + 1) * sizeof(int) + 96;
@@ -803,6 +808,9 @@ neigh_build_tile3_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* _
 
   const unsigned lt_mask = (1u << lane) - 1u;
   int4* dense = s_dense + w * 32;
+  const int tile_q0 = tile_center[(size_t)t * TILE_NCENTER].z;   // first row of the tile (tile_table_kernel)
+  unsigned short* rows_t = rows + (size_t)tile_q0 * tcap;
+  asm volatile("" : "+l"(rows_t));   // keep the sum in registers (ptxas otherwise re-derives it in front of every store)
   const float bsy = (float)B.binsize[1], bsz = (float)B.binsize[2];
   const float ey0 = (float)((by0 - g.sy + B.mbinlo[1]) * B.binsize[1] - (double)org_y);
   const float ez0 = (float)((bz0 - g.sz + B.mbinlo[2]) * B.binsize[2] - (double)org_z);
@@ -863,8 +871,9 @@ neigh_build_tile3_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* _
         const float xA = sx[aA], yA = sy[aA], zA = sz[aA], xB = sx[aB], yB = sy[aB], zB = sz[aB];
         const int tA = UC ? 0 : (int)st[aA], tB = UC ? 0 : (int)st[aB];
         const int qA = ce.z + (aA - ce.x), qB = ce.z + (aB - ce.x);
-        unsigned short* rowA = rows + (size_t)qA * tcap;
-        unsigned short* rowB = rows + (size_t)qB * tcap;
+        // rows of a tile are contiguous: one 64-bit base per CTA, a 32-bit offset per atom
+        unsigned oA = (unsigned)(qA - tile_q0) * (unsigned)tcap, oB = (unsigned)(qB - tile_q0) * (unsigned)tcap;
+        asm volatile("" : "+r"(oA), "+r"(oB));
 
         // ---- candidate interval of the pair in every run ----
         int L = 0, len = 0;
@@ -1001,11 +1010,11 @@ neigh_build_tile3_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* _
             const unsigned mhB = MODE == 0 ? mB : __ballot_sync(0xffffffffu, okB && halfB);
             if (okA) {
               const int pos = nA + __popc(mA & lt_mask);
-              if (pos < tcap) rowA[pos] = (unsigned short)(lc | ((MODE != 0 && halfA) ? TILE_HALF_BIT : 0));
+              if (pos < tcap) stg_u16(rows_t + (oA + (unsigned)pos), (unsigned short)(lc | ((MODE != 0 && halfA) ? TILE_HALF_BIT : 0)));
             }
             if (okB) {
               const int pos = nB + __popc(mB & lt_mask);
-              if (pos < tcap) rowB[pos] = (unsigned short)(lc | ((MODE != 0 && halfB) ? TILE_HALF_BIT : 0));
+              if (pos < tcap) stg_u16(rows_t + (oB + (unsigned)pos), (unsigned short)(lc | ((MODE != 0 && halfB) ? TILE_HALF_BIT : 0)));
             }
             nA += __popc(mA); hA += __popc(mhA);
             nB += __popc(mB); hB += __popc(mhB);
