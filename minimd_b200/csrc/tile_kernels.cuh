@@ -804,17 +804,27 @@ neigh_build_tile3_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* _
       if (!UC) st[off + k] = (unsigned char)lane_to_type(v.w);
     }
   }
+  // the last slot of the window (hcap >= atoms + 8) is a far-away atom: lanes past the end of a sweep test it
+  const int far_slot = g.hcap - 1;
+  if (threadIdx.x == 0) {
+    sx[far_slot] = 3.0e18f; sy[far_slot] = 3.0e18f; sz[far_slot] = 3.0e18f;
+    if (!UC) st[far_slot] = 0;
+  }
   __syncthreads();
 
   const unsigned lt_mask = (1u << lane) - 1u;
-  int4* dense = s_dense + w * 32;
+  // dense intervals of this warp's current pair: {first index - prefix, class | slot0*4} and, apart, the prefix of lengths
+  int2* dense = reinterpret_cast<int2*>(s_dense) + w * 32;
+  int* dpref = reinterpret_cast<int*>(reinterpret_cast<int2*>(s_dense) + TB2_WARPS * 32) + w * 32;
   const int tile_q0 = tile_center[(size_t)t * TILE_NCENTER].z;   // first row of the tile (tile_table_kernel)
   unsigned short* rows_t = rows + (size_t)tile_q0 * tcap;
   asm volatile("" : "+l"(rows_t));   // keep the sum in registers (ptxas otherwise re-derives it in front of every store)
   const float bsy = (float)B.binsize[1], bsz = (float)B.binsize[2];
   const float ey0 = (float)((by0 - g.sy + B.mbinlo[1]) * B.binsize[1] - (double)org_y);
   const float ez0 = (float)((bz0 - g.sz + B.mbinlo[2]) * B.binsize[2] - (double)org_z);
-  const float rc = B.rcull, rc2 = rc * rc, fcut0 = (float)B.cut0, band = B.band;
+  const float rc = B.rcull, rc2 = rc * rc, band = B.band;
+  float fcut0 = (float)B.cut0;
+  asm volatile("" : "+f"(fcut0));   // (keeps the FP64 -> FP32 conversion out of the sweep loop)
   int warp_max_h = 0, warp_max_f = 0;
   unsigned long long warp_total = 0ull;
 
@@ -868,7 +878,9 @@ neigh_build_tile3_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* _
         const int aA = a, aB = two ? a + 1 : a;
         a += two ? 2 : 1;
         if (bad_geom) { if (lane == 0) atomicOr(status, 2); continue; }
-        const float xA = sx[aA], yA = sy[aA], zA = sz[aA], xB = sx[aB], yB = sy[aB], zB = sz[aB];
+        // (a single atom: B sits far away and never finds a neighbor)
+        const float xA = sx[aA], yA = sy[aA], zA = sz[aA];
+        const float xB = two ? sx[aB] : -3.0e18f, yB = two ? sy[aB] : -3.0e18f, zB = two ? sz[aB] : -3.0e18f;
         const int tA = UC ? 0 : (int)st[aA], tB = UC ? 0 : (int)st[aB];
         const int qA = ce.z + (aA - ce.x), qB = ce.z + (aB - ce.x);
         // rows of a tile are contiguous: one 64-bit base per CTA, a 32-bit offset per atom
@@ -917,10 +929,13 @@ neigh_build_tile3_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* _
         }
         const int M = __shfl_sync(0xffffffffu, incl, 31);
         __syncwarp();
-        if (len > 0)  // flags in the two low bits of .z, CSR slot of tile-local index 0 above them
-          dense[__popc(nz & lt_mask)] = make_int4(L - (incl - len), incl - len, r_slot0 * 4 + r_info, 0);
+        if (len > 0) {  // flags in the two low bits of .y, CSR slot of tile-local index 0 above them
+          const int k = __popc(nz & lt_mask);
+          dense[k] = make_int2(L - (incl - len), r_slot0 * 4 + r_info);
+          dpref[k] = incl - len;
+        }
         __syncwarp();
-        const int my_dpref = lane < nd ? dense[lane].y : 0x7fffffff;
+        const int my_dpref = lane < nd ? dpref[lane] : 0x7fffffff;
 
         int nA = 0, hA = 0, nB = 0, hB = 0;
         // one pass over the pair's candidates, 32 per sweep; EXACT adds the FP64 re-test of candidates inside the guard band
@@ -936,9 +951,9 @@ neigh_build_tile3_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* _
             const unsigned starts = __reduce_or_sync(0xffffffffu, starts_here ? (1u << (my_dpref - s0)) : 0u);
             const int before = __popc(__ballot_sync(0xffffffffu, my_dpref < s0));
             const int rr = valid ? before + __popc(starts & ((2u << lane) - 1u)) - 1 : 0;
-            const int4 dv = dense[rr];
-            const int lc = valid ? dv.x + n : aA;
-            const int info = dv.z;
+            const int2 dv = dense[rr];
+            const int lc = valid ? dv.x + n : far_slot;
+            const int info = dv.y;
             const float cxj = sx[lc], cyj = sy[lc], czj = sz[lc];
             T cutA = B.cut0, cutB = B.cut0;
             float fA = fcut0, fB = fcut0;
@@ -955,7 +970,7 @@ neigh_build_tile3_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* _
               } else {
                 const float d = (dx * dx + dy * dy + dz * dz) - fA;
                 okA = d < -band;
-                const bool close = fabsf(d) <= band && lc != aA && valid;
+                const bool close = fabsf(d) <= band && lc != aA;
                 if (!EXACT) closeany = closeany || close;
                 if (EXACT) {
                   if (__any_sync(0xffffffffu, close)) {
@@ -971,7 +986,7 @@ neigh_build_tile3_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* _
               } else {
                 const float d = (dx * dx + dy * dy + dz * dz) - fB;
                 okB = d < -band;
-                const bool close = two && fabsf(d) <= band && lc != aB && valid;
+                const bool close = fabsf(d) <= band && lc != aB;
                 if (!EXACT) closeany = closeany || close;
                 if (EXACT) {
                   if (__any_sync(0xffffffffu, close)) {
@@ -980,8 +995,8 @@ neigh_build_tile3_kernel(const Vec4<T>* __restrict__ x, int nlocal, const int* _
                 }
               }
             }
-            okA = okA && valid && lc != aA;
-            okB = okB && valid && lc != aB && two;
+            okA = okA && lc != aA;
+            okB = okB && lc != aB;
             bool halfA = true, halfB = true;
             if (MODE == 1) {
               const bool own_bin = (info & 1) && (unsigned)(lc - own_lo) < own_n;
