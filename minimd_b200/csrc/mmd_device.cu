@@ -938,6 +938,7 @@ template <class T> struct Impl {
       LJDealtParams<T> Q;
       Q.cutforcesq = P.cutforcesq; Q.sigma6 = P.sigma6; Q.epsilon = P.epsilon;
       Q.k48 = (T)48 * P.epsilon * P.sigma6;
+      Q.kA = Q.k48 * P.sigma6; Q.kB = (T)-0.5 * Q.k48;
       Q.cutforcesq_tab = P.cutforcesq_tab; Q.sigma6_tab = P.sigma6_tab; Q.epsilon_tab = P.epsilon_tab;
       Q.ntypes = P.ntypes; Q.e_scale = P.e_scale; Q.v_scale = P.v_scale;
       MM(smem_optin(c, force_lj_dealt_kernel<T, EV, UNI, INTEG>));

@@ -264,6 +264,7 @@ __device__ __forceinline__ float pair_rcp(float x) { return __frcp_rn(x); }
 template <class T> struct LJDealtParams {
   T cutforcesq, sigma6, epsilon;
   T k48;   // 48 * epsilon * sigma6
+  T kA, kB;  // 48 eps sigma6^2 and -24 eps sigma6: F/r = r^-8 (kA r^-6 + kB), the uniform-parameter form of the line below
   const T* cutforcesq_tab;
   const T* sigma6_tab;
   const T* epsilon_tab;
@@ -298,7 +299,7 @@ __device__ __forceinline__ void lj_pair(const QWin<T>& S, const LJDealtParams<T>
   const T a2 = a1 * a1;
   const T a3 = a2 * a1;
   // F/r = 48 eps sr6 (sr6 - 0.5) / r^2 with sr6 = sigma6 / r^6 (ref/force_lj.cpp:232-235)
-  const T force = (a2 * a2) * (a3 * s6 - (T)0.5) * k48;
+  const T force = UNIFORM ? (a2 * a2) * (a3 * P.kA + P.kB) : (a2 * a2) * (a3 * s6 - (T)0.5) * k48;
   if (hit) {
     fx += dx * force;
     fy += dy * force;
@@ -328,8 +329,8 @@ __device__ __forceinline__ void lj_pair2_f32(const QWin<float>& S, const LJDealt
   const float2 a1 = make_float2(__frcp_rn(rsq.x), __frcp_rn(rsq.y));
   const float2 a2 = __fmul2_rn(a1, a1);
   const float2 a3 = __fmul2_rn(a2, a1);
-  const float2 t = __ffma2_rn(a3, make_float2(P.sigma6, P.sigma6), make_float2(-0.5f, -0.5f));
-  float2 force = __fmul2_rn(__fmul2_rn(__fmul2_rn(a2, a2), t), make_float2(P.k48, P.k48));
+  const float2 t = __ffma2_rn(a3, make_float2(P.kA, P.kA), make_float2(P.kB, P.kB));
+  float2 force = __fmul2_rn(__fmul2_rn(a2, a2), t);
   force.x = rsq.x < P.cutforcesq ? force.x : 0.0f;
   force.y = rsq.y < P.cutforcesq ? force.y : 0.0f;
   fx2 = __ffma2_rn(dx, force, fx2);
