@@ -409,38 +409,32 @@ force_lj_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Ti
     const int2 r = __ldg(tr + (lane % TBY + g.sy) + (lane / TBY + g.sz) * g.nry);
     pcl = make_int4(ce.x, ce.y - ce.x, ce.z, r.x - r.y);
   }
-  const int np_l = (pcl.y + 3) >> 2;
-  int my_end = np_l;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, my_end, o);
-    if (lane >= o) my_end += v;
-  }
-  const int NP = __shfl_sync(0xffffffffu, my_end, 31);
-  const int my_beg = my_end - np_l;
-  if (lane >= TILE_NCENTER) my_end = 0x7fffffff;
   const int qtile0 = __shfl_sync(0xffffffffu, pcl.z, 0);
   const int nrows = __shfl_sync(0xffffffffu, pcl.z + pcl.y, TILE_NCENTER - 1) - qtile0;
   if (w == 0 && lane < TILE_NCENTER) S.pc[lane] = pcl;  // for the epilogue (read after the barriers below)
+  // row j of the tile -> {tile-local index of its atom, centre pencil}: the rows of a tile are numbered pencil by
+  // pencil (tile_table_kernel), so a pass is simply four consecutive rows
+  for (int c = w; c < TILE_NCENTER; c += nw) {
+    const int lo = __shfl_sync(0xffffffffu, pcl.x, c), cnt = __shfl_sync(0xffffffffu, pcl.y, c);
+    const int r0 = __shfl_sync(0xffffffffu, pcl.z, c) - qtile0;
+    for (int k = lane; k < cnt; k += 32) S.stash_a[r0 + k] = (lo + k) | (c << 16);
+  }
+  const int NP = (nrows + 3) >> 2;
 
-  // pass list: pass i of the tile belongs to the pencil c with beg[c] <= i < end[c]
+  // pass i of the tile: rows 4i .. 4i+3, one per quarter warp
   int2 ta_n = make_int2(-1, 0);
   unsigned long long w_n = sent4;
-  int a_n = 0, q_n = 0, c_n = 0;
+  int j_n = 0;
   bool have_n = false;
   auto locate = [&](int i) {  // fills the *_n state for pass i (warp-uniform i)
-    c_n = min(__popc(__ballot_sync(0xffffffffu, my_end <= i)), TILE_NCENTER - 1);
-    const int lo = __shfl_sync(0xffffffffu, pcl.x, c_n), cnt = __shfl_sync(0xffffffffu, pcl.y, c_n);
-    const int q0 = __shfl_sync(0xffffffffu, pcl.z, c_n), beg = __shfl_sync(0xffffffffu, my_beg, c_n);
-    const int k = (i - beg) * 4 + qg;
-    have_n = i < NP && k < cnt;
+    const int j = i * 4 + qg;
+    have_n = j < nrows;
+    j_n = have_n ? j : 0;
     ta_n = make_int2(-1, 0);
     w_n = sent4;
-    a_n = lo + (have_n ? k : 0);
-    q_n = q0 + (have_n ? k : 0);
     if (have_n) {
-      ta_n = __ldg(row_atom + q_n);
-      w_n = ldg_rowq(rowsq + (size_t)q_n * wpr + p);
+      ta_n = __ldg(row_atom + (qtile0 + j));
+      w_n = ldg_rowq(rowsq + (size_t)(qtile0 + j) * wpr + p);
     }
   };
   locate(w);
@@ -456,7 +450,8 @@ force_lj_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Ti
   double eng = 0.0, vir = 0.0, ke = 0.0;
   for (int i = w; i < NP; i += nw) {
     const bool have = have_n;
-    const int a = a_n, q = q_n, c = c_n;
+    const int j = j_n, q = qtile0 + j;
+    const int a = S.stash_a[j] & 0xffff;
     const int2 ta = ta_n;
     // an atom owns its row whatever the row's length (an isolated atom has an empty one and still integrates)
     const bool own = have && ta.x >= 0 && ta.x < nlocal;
@@ -509,14 +504,18 @@ force_lj_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Ti
       fy += fy2.x + fy2.y;
       fz += fz2.x + fz2.y;
     }
-    fx = group_sum<QL>(fx);
-    fy = group_sum<QL>(fy);
-    fz = group_sum<QL>(fz);
-    if (p == 0 && have) {
-      const int j = q - qtile0;
-      T* s = S.stash_f + j * 3;
-      s[0] = fx; s[1] = fy; s[2] = fz;
-      S.stash_a[j] = a | (c << 16);
+    // the three sums over the atom's eight lanes, as one butterfly that halves the number of values a lane carries at
+    // every step: lanes 0,2,4 of the quarter warp end up with F_x, F_y, F_z
+    {
+      const bool hi4 = (p & 4) != 0, hi2 = (p & 2) != 0;
+      const T s1 = __shfl_xor_sync(0xffffffffu, hi4 ? fx : fz, 4, 32);
+      const T s2 = __shfl_xor_sync(0xffffffffu, fy, 4, 32);
+      const T A = (hi4 ? fz : fx) + s1;        // lanes 0-3: x, lanes 4-7: z
+      const T B = hi4 ? (T)0 : fy + s2;        // lanes 0-3: y
+      const T s3 = __shfl_xor_sync(0xffffffffu, hi2 ? A : B, 2, 32);
+      T C = (hi2 ? B : A) + s3;                // lanes 0,1: x   2,3: y   4,5: z   6,7: 0
+      C += __shfl_xor_sync(0xffffffffu, C, 1, 32);
+      if (have && !(p & 1) && p < 6) S.stash_f[j * 3 + (p >> 1)] = C;
     }
   }
   __syncthreads();
