@@ -99,19 +99,7 @@ eam_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, TileGeo
       const int2 r = __ldg(tr + (lane % TBY + g.sy) + (lane / TBY + g.sz) * g.nry);
       slot0 = r.x - r.y;
     }
-    const int n = ce.y - ce.x;
-    const int np = (n + 3) >> 2;
-    int incl = np;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane < TILE_NCENTER) {
-      S.pc[lane] = make_int4(ce.x, n, ce.z, slot0);
-      S.pp[lane] = incl - np;
-    }
-    if (lane == TILE_NCENTER) S.pp[TILE_NCENTER] = incl;
+    if (lane < TILE_NCENTER) S.pc[lane] = make_int4(ce.x, ce.y - ce.x, ce.z, slot0);
   }
   __syncthreads();
   const unsigned tab_bytes = (unsigned)(PASS == 1 ? D.bytes1() : D.bytes2());
@@ -130,28 +118,28 @@ eam_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, TileGeo
     }
   }
 
-  const int NP = S.pp[TILE_NCENTER];
-  const int my_end = lane < TILE_NCENTER ? S.pp[lane + 1] : 0x7fffffff;
+  // row j of the tile -> {tile-local index of its atom, centre pencil}: the rows of a tile are numbered pencil by
+  // pencil (tile_table_kernel), so a pass is simply four consecutive rows
   const int qtile0 = S.pc[0].z;
+  const int nrows = S.pc[TILE_NCENTER - 1].z + S.pc[TILE_NCENTER - 1].y - qtile0;
+  for (int c = w; c < TILE_NCENTER; c += nw) {
+    const int4 pc = S.pc[c];
+    for (int k = lane; k < pc.y; k += 32) S.stash_a[pc.z - qtile0 + k] = (pc.x + k) | (c << 16);
+  }
+  const int NP = (nrows + 3) >> 2;
   int2 ta_n = make_int2(-1, 0);
   unsigned long long w_n = sent4;
-  int a_n = 0, q_n = 0, c_n = 0;
+  int j_n = 0;
   bool have_n = false;
   auto locate = [&](int i) {
-    c_n = __popc(__ballot_sync(0xffffffffu, my_end <= i));
-    have_n = false;
+    const int j = i * 4 + qg;
+    have_n = j < nrows;
+    j_n = have_n ? j : 0;
     ta_n = make_int2(-1, 0);
     w_n = sent4;
-    if (i < NP) {
-      const int4 pc = S.pc[c_n];
-      const int k = (i - S.pp[c_n]) * 4 + qg;
-      have_n = k < pc.y;
-      a_n = pc.x + (have_n ? k : 0);
-      q_n = pc.z + (have_n ? k : 0);
-      if (have_n) {
-        ta_n = __ldg(row_atom + q_n);
-        w_n = ldg_rowq(rowsq + (size_t)q_n * wpr + p);
-      }
+    if (have_n) {
+      ta_n = __ldg(row_atom + (qtile0 + j));
+      w_n = ldg_rowq(rowsq + (size_t)(qtile0 + j) * wpr + p);
     }
   };
   locate(w);
@@ -166,7 +154,8 @@ eam_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, TileGeo
   const int nr = E.nr;
   for (int i = w; i < NP; i += nw) {
     const bool have = have_n;
-    const int a = a_n, q = q_n, c = c_n;
+    const int j = j_n, q = qtile0 + j;
+    const int a = S.stash_a[j] & 0xffff;
     const int2 ta = ta_n;
     const bool own = have && ta.x >= 0 && ta.x < nlocal;
     const int n = own ? max(ta.y, 0) : 0;
@@ -239,20 +228,26 @@ eam_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, TileGeo
       pair((int)((w0 >> 16) & 0x7fffull));
     }
     if (gmax & 1) pair((int)((w0 >> ((gmax & 2) * 16)) & 0x7fffull));
-    ax = group_sum<QL>(ax);
-    if (PASS == 2) { ay = group_sum<QL>(ay); az = group_sum<QL>(az); }
-    if (p == 0 && have) {
-      const int j = q - qtile0;
-      T* s = S.stash_f + j * 3;
-      s[0] = ax;
-      if (PASS == 2) { s[1] = ay; s[2] = az; }
-      S.stash_a[j] = a | (c << 16);
+    if (PASS == 1) {
+      ax = group_sum<QL>(ax);
+      if (p == 0 && have) S.stash_f[j * 3] = ax;
+    } else {
+      // the three sums over the atom's eight lanes, as one butterfly that halves the number of values a lane carries
+      // at every step: lanes 0,2,4 of the quarter warp end up with F_x, F_y, F_z
+      const bool hi4 = (p & 4) != 0, hi2 = (p & 2) != 0;
+      const T s1 = __shfl_xor_sync(0xffffffffu, hi4 ? ax : az, 4, 32);
+      const T s2 = __shfl_xor_sync(0xffffffffu, ay, 4, 32);
+      const T A = (hi4 ? az : ax) + s1;
+      const T B = hi4 ? (T)0 : ay + s2;
+      const T s3 = __shfl_xor_sync(0xffffffffu, hi2 ? A : B, 2, 32);
+      T C = (hi2 ? B : A) + s3;
+      C += __shfl_xor_sync(0xffffffffu, C, 1, 32);
+      if (have && !(p & 1) && p < 6) S.stash_f[j * 3 + (p >> 1)] = C;
     }
   }
   __syncthreads();
 
   // ---- phase 3: one thread per row of the tile ----
-  const int nrows = S.pc[TILE_NCENTER - 1].z + S.pc[TILE_NCENTER - 1].y - qtile0;
   for (int j = tid; j < nrows; j += blockDim.x) {
     const int2 ta = __ldg(row_atom + (size_t)(qtile0 + j));
     if (ta.x < 0 || ta.x >= nlocal) continue;
