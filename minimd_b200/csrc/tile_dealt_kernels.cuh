@@ -139,7 +139,7 @@ tile_rows_deal_kernel(const unsigned short* __restrict__ rows, const int2* __res
     const unsigned base1 = c1 * 0x01010100u + ((c0 * 0x01010101u) >> 24) * 0x01010101u;
     unsigned p0 = base0 + (c0 - snap0), p1 = base1 + (c1 - snap1);   // + the class members in the words [0, rot): no byte carries
     const int G = (n + QL - 1) / QL;
-    const float rG = 1.0f / (float)G;
+    const unsigned invG = 65536u / (unsigned)G + 1u;   // t / G == (t * invG) >> 16 for t < 256, G <= 32 (checked exhaustively)
     unsigned short* dst = reinterpret_cast<unsigned short*>(s_dst + threadIdx.x * dstride);
     auto place = [&](unsigned ent) {
       const unsigned sh = (ent & 3u) << 3;
@@ -149,8 +149,7 @@ tile_rows_deal_kernel(const unsigned short* __restrict__ rows, const int2* __res
       const unsigned inc = 1u << sh;
       p0 += hi ? 0u : inc;
       p1 += hi ? inc : 0u;
-      // t / G for t < 256: (t + 0.5) / G stays >= 0.5 / G away from every integer, far above the FP32 error
-      const int p = __float2int_rd(((float)t + 0.5f) * rG);
+      const int p = (int)(((unsigned)t * invG) >> 16);
       const int g = t - p * G;
       dst[((g >> 2) << 5) + (p << 2) + (g & 3)] = (unsigned short)ent;   // the half-list flag (bit 15) travels along
     };
