@@ -1,5 +1,6 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_host.py tests/test_gpu_dropin.py -x -q -m gpu 2>&1 | tail -3
+python tools/gpu/det_check.py 60 2>&1 | tail -4
+timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_host.py -x -q -m gpu 2>&1 | tail -3
 timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/r2_bench26.json 2> gpurun_out/r2_bench26.err
 python - <<'PY'
 import json
