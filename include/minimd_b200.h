@@ -213,6 +213,7 @@ int mmd_query_int(mmd_ctx* ctx, const char* key, long long* value);
  *   "tile_xsort" (1)   tile lists: every bin of the windows' private slot map sorted by x + interval build; 0 = windows in
  *                      CSR order + per-bin candidate-table build
  *   "tile_build2" (1)  0 = tile rows from the warp-per-bin build (no shared-memory window; testing / odd geometries)
+ *   "tile_pair_build" (1)  interval build: two atoms of a bin share one sweep over the union of their candidate intervals
  *   "tile_lane_build" (0)  interval build with one lane per atom instead of one warp per atom (measured slower)
  *   "tile_eam" (0)     tile-resident lists for the EAM force too (measured slower than the classic kernels)
  *   "force_nonuniform" (0)  testing: use the per-type parameter-table kernels even when all type pairs are equal
@@ -221,14 +222,20 @@ int mmd_query_int(mmd_ctx* ctx, const char* key, long long* value);
  *   "fuse_halo" (1)       one rank: forward halo in one launch (ghosts resolved to their local source)
  *   "fuse_ghosts" (0)     one rank, dealt LJ lists: the fused force kernel also writes every atom's periodic images, so
  *                         the forward halo of the next step needs no launch at all (measured slower: off by default)
+ *   "graph_steps" (1)     mmd_run on one rank: two consecutive plain steps (forward halo + fused force/Verlet kernel, no rebuild,
+ *                         no thermo) are captured once per neighbor list as a CUDA graph and replayed for the steps up to the
+ *                         next rebuild (ref/integrate.cpp:88-205 runs the same sequence every step).  0: launch every step;
+ *                         1: only with at most 262 144 local atoms (small decks, where launch latency shows); 2: whenever it applies.
  *   "p2p_halo" (1)        several ranks: forward halo over CUDA-IPC peer windows; 0 = NCCL send/recv
  *   "split_force" (1)     several ranks, dealt LJ lists: tiles without ghosts in their halo window run on a second stream
  *                         while the forward halo of the step is in flight; boundary tiles follow the halo
  *   "lj_threads_per_atom" (0 = auto), "eam_threads_per_atom" (8): lanes per atom of the classic kernels
  *   "phase_timing" (0)    per-phase CUDA-event timing of mmd_run
+ *   "kernel_profile" (0)  diagnostic builds (-DMMD_KERNEL_PROFILE) only: the LJ tile force kernels sum clock64 differences
+ *                         (staging, CTA life, CTA count), read back with the queries "stage_clocks", "cta_clocks", "cta_count"
  * Queries added by these paths: "list_tile", "list_dealt", "list_xsorted", "tile_ok", "tile_builds", "tile_fallbacks",
  * "tile_max_halo", "tile_max_full", "tile_row_capacity", "tile_dealt_capacity", "tile_count", "tile_interior",
- * "tile_boundary", "split_steps", "fused_halo_steps", "p2p_active", "p2p_calls". */
+ * "tile_boundary", "split_steps", "fused_halo_steps", "graph_captures", "graph_replays", "p2p_active", "p2p_calls". */
 int mmd_set_option(mmd_ctx* ctx, const char* key, long long value);
 
 #ifdef __cplusplus

@@ -236,6 +236,15 @@ struct mmd_ctx {
   bool ghosts_fresh = false;      // the last launch already wrote the ghosts of the next step
   DevBuf img_start, img_cursor, img_list;
   long long fused_halo_steps = 0;
+  // CUDA graph of two consecutive plain steps (forward halo + fused force/Verlet, twice: the position buffers and the
+  // mirror end where they started), replayed for the steps between two rebuilds.  Option "graph_steps": 0 off,
+  // 1 (default) one rank and at most GRAPH_AUTO_ATOMS local atoms (small decks: launch latency), 2 whenever it applies
+  int graph_steps = 1;
+  cudaGraphExec_t pair_exec = nullptr;
+  bool pair_valid = false;        // pair_exec matches the current lists, counts and buffer orientation
+  bool capturing = false;         // no phase marks while the stream is in capture mode
+  long long pair_launches = 0;    // kernels per replay
+  long long graph_replays = 0, graph_captures = 0;
   bool fuse_halo = true;          // option "fuse_halo"
   DevBuf sendbuf, recvbuf;
   DevBuf exch_flag, exch_pos, exch_holes;
@@ -281,7 +290,7 @@ struct mmd_ctx {
 
 // close the interval since the previous mark and attribute it to `phase` (-1: just open an interval)
 static int phase_mark(mmd_ctx* c, int phase) {
-  if (!c->phase_timing) return MMD_OK;
+  if (!c->phase_timing || c->capturing) return MMD_OK;
   if (c->nmarks == (int)c->marks.size()) {
     cudaEvent_t e;
     CU(cudaEventCreate(&e));
@@ -1578,6 +1587,55 @@ template <class T> struct Impl {
     return MMD_OK;
   }
 
+  // ---- CUDA graph of two plain steps ------------------------------------------------------
+  static constexpr int GRAPH_AUTO_ATOMS = 262144;
+  static bool graph_usable(mmd_ctx* c, const mmd_run_params* p) {
+    if (!c->graph_steps || c->nranks != 1 || c->fuse_ghosts || c->kernel_profile) return false;
+    if (c->graph_steps == 1 && c->nlocal > GRAPH_AUTO_ATOMS) return false;
+    if (!(c->fuse_force && c->fuse_integrate && c->list_tile && c->neigh_rows == c->nlocal)) return false;
+    if (p->force_style != 0 && !eam_dealt_fits(c)) return false;
+    if (c->list_dealt && !c->xs_valid) return false;
+    for (int w = 0; w < c->swaps.nswap; w++)
+      if (!is_self(c, w)) return false;
+    return true;
+  }
+  // the body of a plain step, as the eager loop runs it
+  static int plain_step_body(mmd_ctx* c, const mmd_run_params* p) {
+    if (!c->ghosts_fresh) MM(communicate(c, false));
+    c->ghosts_fresh = false;
+    if (p->force_style == 0) MM(lj_tile_verlet(c, p->halfneigh, 0, p->dt, p->dtforce, p->mass));
+    else MM(eam_dealt_verlet(c, p->halfneigh, 0, p->dt, p->dtforce, p->mass));
+    return MMD_OK;
+  }
+  static int capture_pair(mmd_ctx* c, const mmd_run_params* p) {
+    const long long l0 = c->launches;
+    CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+    c->capturing = true;
+    int rc = plain_step_body(c, p);
+    if (rc == MMD_OK) rc = plain_step_body(c, p);
+    c->capturing = false;
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    c->pair_launches = c->launches - l0;
+    c->launches = l0;
+    if (rc != MMD_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess || !g) return set_err(MMD_ERR_CUDA, "graph capture of two steps: %s", cudaGetErrorString(e));
+    bool have = false;
+    if (c->pair_exec) {  // same topology as the previous neighbor list's graph: update in place
+      cudaGraphExecUpdateResultInfo info;
+      have = cudaGraphExecUpdate(c->pair_exec, g, &info) == cudaSuccess;
+      if (!have) { cudaGetLastError(); cudaGraphExecDestroy(c->pair_exec); c->pair_exec = nullptr; }
+    }
+    if (!have) {
+      const cudaError_t ei = cudaGraphInstantiate(&c->pair_exec, g, 0);
+      if (ei != cudaSuccess) { cudaGraphDestroy(g); c->pair_exec = nullptr; return set_err(MMD_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ei)); }
+    }
+    cudaGraphDestroy(g);
+    c->pair_valid = true;
+    c->graph_captures++;
+    return MMD_OK;
+  }
+
   // ---- fused time loop -------------------------------------------------------------------
   static int run(mmd_ctx* c, const mmd_run_params* p, mmd_thermo_sample* samples, int max_samples, int* nsamples,
                  float* elapsed_ms) {
@@ -1588,6 +1646,12 @@ template <class T> struct Impl {
     if (elapsed_ms) CU(cudaEventRecord(c->ev0, c->stream));
     MM(phase_mark(c, -1));
     const int last = p->first_step + p->ntimes - 1;
+    c->pair_valid = false;  // (dt, masses and list style are the caller's: never reuse a graph across calls)
+    // a step with nothing but the forward halo and the fused force / Verlet kernel
+    auto plain_step = [&](int m) {
+      const int evm = p->thermo_nstat > 0 ? ((m + 1) % p->thermo_nstat == 0) : 0;
+      return ((m + 1) % p->neigh_every) != 0 && m != p->first_step && m < last && !evm;
+    };
     for (int n = p->first_step; n < p->first_step + p->ntimes; n++) {
       // (from the second step on, initialIntegrate already ran fused with the previous finalIntegrate)
       if (n == p->first_step || !c->fuse_integrate) {
@@ -1604,6 +1668,18 @@ template <class T> struct Impl {
         continue;
       }
       MM(split_join(c));
+      // two plain steps in a row on one rank: one graph launch (captured once per neighbor list)
+      if (plain_step(n) && plain_step(n + 1) && graph_usable(c, p)) {
+        if (!c->pair_valid) MM(capture_pair(c, p));
+        CU(cudaGraphLaunch(c->pair_exec, c->stream));
+        c->launches += c->pair_launches;
+        c->graph_replays++;
+        c->ghosts_fresh = false;
+        MM(phase_mark(c, MMD_PHASE_FORCE));  // (halo, force and Verlet halves of both steps)
+        n++;
+        continue;
+      }
+      c->pair_valid = false;  // an eager step changes the buffer orientation or the lists
       if ((n + 1) % p->neigh_every) {
         // (the fused force kernel of the previous step may have written this step's ghosts already)
         if (!c->ghosts_fresh) MM(communicate(c, false));
@@ -1891,6 +1967,7 @@ int mmd_ctx_destroy(mmd_ctx* c) {
                     &c->rho, &c->fp, &c->border_tiles, &c->sendbuf, &c->recvbuf, &c->exch_flag, &c->exch_pos,
                     &c->exch_holes, &c->ghost_src, &c->ghost_shift, &c->sruns, &c->tile_runs, &c->tile_center, &c->tile_info, &c->tile_slots, &c->tile_oslot, &c->trows,
                     &c->tnum, &c->trowsq, &c->xs_rec[0], &c->xs_rec[1], &c->xs_z[0], &c->xs_z[1], &c->slot_of, &c->xs_types, &c->eam_blob1, &c->eam_blob2, &c->fp_s, &c->tile_split, &c->send_flag, &c->img_start, &c->img_cursor, &c->img_list};
+  if (c->pair_exec) cudaGraphExecDestroy(c->pair_exec);
   for (DevBuf* b : bufs) b->release();
   for (int w = 0; w < MMD_MAX_SWAPS; w++) c->sw[w].list.release();
   for (int r = 0; r < (int)c->peer_win.size(); r++)
@@ -2370,6 +2447,8 @@ int mmd_query_int(mmd_ctx* c, const char* key, long long* value) {
   else if (k == "tile_dealt_capacity") *value = c->tcapq;
   else if (k == "split_steps") *value = c->split_steps;
   else if (k == "fused_halo_steps") *value = c->fused_halo_steps;
+  else if (k == "graph_replays") *value = c->graph_replays;
+  else if (k == "graph_captures") *value = c->graph_captures;
   else if (k == "stage_clocks" || k == "cta_clocks" || k == "cta_count") {
     unsigned long long h[4] = {0, 0, 0, 0};
     if (c->d_prof) {
@@ -2416,6 +2495,10 @@ int mmd_set_option(mmd_ctx* c, const char* key, long long value) {
     }
     if (c->d_prof) cudaMemset(c->d_prof, 0, 4 * sizeof(unsigned long long));
     c->kernel_profile = value != 0;
+  } else if (k == "graph_steps") {  // 0: launch every step; 1: graph pairs of plain steps on small single-rank decks; 2: whenever possible
+    if (value < 0 || value > 2) return set_err(MMD_ERR_ARG, "graph_steps must be 0, 1 or 2");
+    c->graph_steps = (int)value;
+    c->pair_valid = false;
   } else if (k == "split_force") {  // several ranks: interior tiles on a second stream behind the forward halo
     c->split_enable = value != 0;
     if (!c->split_enable) c->split_ready = false;

@@ -403,6 +403,28 @@ def test_time_loop_matches_oracle(force, half, gn, prec, tol, tile):
         assert c.query("maxneighs") == o.geti("maxneighs")
 
 
+@pytest.mark.parametrize("force,half,prec", [("lj", 1, "f64"), ("lj", 0, "f32"), ("eam", 0, "f64")])
+def test_graph_replay_is_the_eager_loop(force, half, prec):
+    """Option graph_steps: pairs of plain steps replayed from a CUDA graph (captured once per neighbor list) must leave
+    exactly the state of the step-by-step launches -- same kernels, same arguments, same count."""
+    def run(graph):
+        cfg = Config(nx=8, ny=8, nz=8, ntimes=70, force=force, halfneigh=half, ghost_newton=half, thermo_nstat=30)
+        o = Oracle(cfg, prec)
+        c = context_from_oracle(o)
+        c.set_option("graph_steps", graph)
+        c.exchange()
+        c.borders()
+        c.build(half, half, 100)
+        samples, _ = c.run(run_params(o, 70))
+        d = c.download("xv", count=c.counts()[0])
+        return samples, d["x"], d["v"], c.query("launches"), c.query("graph_replays"), c.query("graph_captures")
+    eager, graph = run(0), run(2)
+    assert eager[4] == 0 and graph[4] > 20 and 0 < graph[5] <= 6, (eager[4:], graph[4:])
+    assert np.array_equal(eager[1], graph[1]) and np.array_equal(eager[2], graph[2])
+    assert list(eager[0]) == list(graph[0])
+    assert eager[3] == graph[3], "a replay accounts for the launches it stands for"
+
+
 @pytest.mark.parametrize("opts", [dict(tile_lists=1, tile_dealt=1), dict(tile_lists=1, tile_dealt=0),
                                   dict(tile_lists=1, tile_dealt=1, fuse_force=0), dict(tile_lists=0)])
 def test_isolated_atoms_are_still_integrated(opts):
