@@ -19,7 +19,9 @@ e2e     : the same neighbor cycle through the C ABI with HOST buffers: every ste
 roofline: the force launch of one MD step (the dominant kernel; with tile lists it also performs the
           two velocity-Verlet halves) -- algorithmic bytes per launch (SURVEY.md 8d row formulas with
           the neighbor count measured in this run) / its CUDA-event duration inside the timed region,
-          against MEASURED_PEAKS.json's HBM copy bandwidth.  `fp64_frac`: pair evaluations per second
+          against MEASURED_PEAKS.json's HBM copy bandwidth.  (One rank replays pairs of plain steps from
+          a CUDA graph: the events then sit around a pair, and the force launch is charged with the two
+          7-us halo launches inside -- `halo_in_force_interval`.)  `fp64_frac`: pair evaluations per second
           against the measured FP64 pair rate (profiles/r2_fp64_peak.json, tools/microbench/
           fp64_fma_bench.cu).  `traffic`: DRAM bytes per launch from the committed ncu capture of THIS
           kernel on THIS workload (profiles/traffic.json names kernel, atoms and source) or null.
@@ -395,6 +397,9 @@ def measure_resident(a, D, sim, ctx, local_rank, with_clocks):
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "list_format": fmt, "fused_verlet": fused_verlet,
                 "halo_overlapped_in_timing": bool(split_steps > 0),
+                # one rank: pairs of plain steps are replayed from a CUDA graph; the events sit around a pair, so the force
+                # interval then also holds the two 7-us halo launches (the force launch is charged with them)
+                "halo_in_force_interval": bool(ctx.query("graph_replays") > 0),
                 "algorithmic_bytes_per_atom": per_atom, "algorithmic_bytes_per_launch": force_bytes,
                 "avg_launch_ms": force_avg_ms, "launches_timed": f_calls,
                 "neighbors_per_atom": n_per_atom, "peak_source": peak_src,

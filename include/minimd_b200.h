@@ -224,8 +224,7 @@ int mmd_query_int(mmd_ctx* ctx, const char* key, long long* value);
  *                         the forward halo of the next step needs no launch at all (measured slower: off by default)
  *   "graph_steps" (1)     mmd_run on one rank: two consecutive plain steps (forward halo + fused force/Verlet kernel, no rebuild,
  *                         no thermo) are captured once per neighbor list as a CUDA graph and replayed for the steps up to the
- *                         next rebuild (ref/integrate.cpp:88-205 runs the same sequence every step).  0: launch every step;
- *                         1: only with at most 262 144 local atoms (small decks, where launch latency shows); 2: whenever it applies.
+ *                         next rebuild (ref/integrate.cpp:88-205 runs the same sequence every step).  0: launch every step.
  *   "p2p_halo" (1)        several ranks: forward halo over CUDA-IPC peer windows; 0 = NCCL send/recv
  *   "split_force" (1)     several ranks, dealt LJ lists: tiles without ghosts in their halo window run on a second stream
  *                         while the forward halo of the step is in flight; boundary tiles follow the halo

@@ -238,7 +238,7 @@ struct mmd_ctx {
   long long fused_halo_steps = 0;
   // CUDA graph of two consecutive plain steps (forward halo + fused force/Verlet, twice: the position buffers and the
   // mirror end where they started), replayed for the steps between two rebuilds.  Option "graph_steps": 0 off,
-  // 1 (default) one rank and at most GRAPH_AUTO_ATOMS local atoms (small decks: launch latency), 2 whenever it applies
+  // 1 (default) on one rank
   int graph_steps = 1;
   cudaGraphExec_t pair_exec = nullptr;
   bool pair_valid = false;        // pair_exec matches the current lists, counts and buffer orientation
@@ -282,23 +282,25 @@ struct mmd_ctx {
   bool fuse_force = true;      // mmd_run, tile-resident lists: ... and both inside the force kernel's epilogue
   bool phase_timing = false;
   std::vector<cudaEvent_t> marks;
-  std::vector<int> mark_phase;
+  std::vector<int> mark_phase, mark_calls;
   int nmarks = 0;
   double phase_ms[MMD_NPHASE] = {0, 0, 0, 0, 0};
   long long phase_calls[MMD_NPHASE] = {0, 0, 0, 0, 0};
 };
 
 // close the interval since the previous mark and attribute it to `phase` (-1: just open an interval)
-static int phase_mark(mmd_ctx* c, int phase) {
+static int phase_mark(mmd_ctx* c, int phase, int calls = 1 /* force launches etc. the interval stands for */) {
   if (!c->phase_timing || c->capturing) return MMD_OK;
   if (c->nmarks == (int)c->marks.size()) {
     cudaEvent_t e;
     CU(cudaEventCreate(&e));
     c->marks.push_back(e);
     c->mark_phase.push_back(-1);
+    c->mark_calls.push_back(1);
   }
   CU(cudaEventRecord(c->marks[c->nmarks], c->stream));
   c->mark_phase[c->nmarks] = phase;
+  c->mark_calls[c->nmarks] = calls;
   c->nmarks++;
   return MMD_OK;
 }
@@ -311,7 +313,7 @@ static int phase_collect(mmd_ctx* c) {
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, c->marks[k - 1], c->marks[k]));
     c->phase_ms[ph] += ms;
-    c->phase_calls[ph]++;
+    c->phase_calls[ph] += c->mark_calls[k];
   }
   c->nmarks = 0;
   return MMD_OK;
@@ -1588,10 +1590,8 @@ template <class T> struct Impl {
   }
 
   // ---- CUDA graph of two plain steps ------------------------------------------------------
-  static constexpr int GRAPH_AUTO_ATOMS = 262144;
   static bool graph_usable(mmd_ctx* c, const mmd_run_params* p) {
     if (!c->graph_steps || c->nranks != 1 || c->fuse_ghosts || c->kernel_profile) return false;
-    if (c->graph_steps == 1 && c->nlocal > GRAPH_AUTO_ATOMS) return false;
     if (!(c->fuse_force && c->fuse_integrate && c->list_tile && c->neigh_rows == c->nlocal)) return false;
     if (p->force_style != 0 && !eam_dealt_fits(c)) return false;
     if (c->list_dealt && !c->xs_valid) return false;
@@ -1675,7 +1675,7 @@ template <class T> struct Impl {
         c->launches += c->pair_launches;
         c->graph_replays++;
         c->ghosts_fresh = false;
-        MM(phase_mark(c, MMD_PHASE_FORCE));  // (halo, force and Verlet halves of both steps)
+        MM(phase_mark(c, MMD_PHASE_FORCE, 2));  // (halo, force and Verlet halves of both steps)
         n++;
         continue;
       }
@@ -2495,9 +2495,8 @@ int mmd_set_option(mmd_ctx* c, const char* key, long long value) {
     }
     if (c->d_prof) cudaMemset(c->d_prof, 0, 4 * sizeof(unsigned long long));
     c->kernel_profile = value != 0;
-  } else if (k == "graph_steps") {  // 0: launch every step; 1: graph pairs of plain steps on small single-rank decks; 2: whenever possible
-    if (value < 0 || value > 2) return set_err(MMD_ERR_ARG, "graph_steps must be 0, 1 or 2");
-    c->graph_steps = (int)value;
+  } else if (k == "graph_steps") {  // 0: launch every step; 1: one rank replays pairs of plain steps from a CUDA graph
+    c->graph_steps = value != 0;
     c->pair_valid = false;
   } else if (k == "split_force") {  // several ranks: interior tiles on a second stream behind the forward halo
     c->split_enable = value != 0;

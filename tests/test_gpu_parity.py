@@ -418,10 +418,12 @@ def test_graph_replay_is_the_eager_loop(force, half, prec):
         samples, _ = c.run(run_params(o, 70))
         d = c.download("xv", count=c.counts()[0])
         return samples, d["x"], d["v"], c.query("launches"), c.query("graph_replays"), c.query("graph_captures")
-    eager, graph = run(0), run(2)
+    eager, graph = run(0), run(1)
     assert eager[4] == 0 and graph[4] > 20 and 0 < graph[5] <= 6, (eager[4:], graph[4:])
     assert np.array_equal(eager[1], graph[1]) and np.array_equal(eager[2], graph[2])
-    assert list(eager[0]) == list(graph[0])
+    # (energy / virial are summed over CTAs with floating-point atomics: equal up to the order of that sum)
+    for a, b in zip(eager[0], graph[0]):
+        assert a[0] == b[0] and all(abs(u - w) <= 1e-13 * abs(u) for u, w in zip(a[1:], b[1:])), (a, b)
     assert eager[3] == graph[3], "a replay accounts for the launches it stands for"
 
 

@@ -1,0 +1,14 @@
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_host.py tests/test_gpu_dropin.py -x -q -m gpu 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 1200 python bench.py > gpurun_out/r2_bench37.json 2> gpurun_out/r2_bench37.err
+python - <<'PY'
+import json
+try:
+    d=json.loads([l for l in open("gpurun_out/r2_bench37.json") if l.startswith("{")][-1])
+    print(round(d["value"],1), round(d["ms_per_step"],4), d["phase_ms_per_step"], d["roofline"]["avg_launch_ms"], d["roofline"]["launches_timed"], d["roofline"]["frac"], d["roofline"].get("fp64_frac"), d["roofline"]["halo_in_force_interval"], round(d["e2e"]["value"],1), round(d["cpu_baseline"]["value"],2), d["gpu_launches"])
+    for k,v in d.get("other_configs",{}).items():
+        print(k, v.get("error") or (round(v["value"],1), v["phase_ms_per_step"], v["roofline"]["frac"], round(v["e2e"]["value"],1)))
+except Exception as e:
+    print("ERR", e, open("gpurun_out/r2_bench37.err").read()[-3000:])
+PY
