@@ -188,9 +188,9 @@ template <class T> struct QWin {
   QRec<T>* rec;
   T* z;                // FP64 only
   T* stash_f;          // [scap][3]
-  int* stash_a;        // [scap] tile-local index | centre pencil << 16
+  int* stash_a;        // [scap] row of the tile -> tile-local index of its atom | centre pencil << 16 (the pass table)
   int4* pc;            // [16] centre pencils: {first tile-local index, atoms, first row, CSR slot of tile-local index 0}
-  int* pp;             // [17] exclusive prefix of the pencils' pass counts
+  int* pp;             // [17] (unused since the passes are four consecutive rows; keeps the layout of the tables)
   int* run_start;      // [TILE_MAXRUN]
   int* run_off;        // [TILE_MAXRUN + 1]
   unsigned long long* bar;
@@ -343,8 +343,8 @@ __device__ __forceinline__ void lj_pair2_f32(const QWin<float>& S, const LJDealt
 // Phases of a CTA (one tile):
 //   1. thread p < nrun issues ONE bulk copy for pencil run p of the halo window (mirror -> shared memory, 16-byte
 //      records); FP64 z values follow as 8-byte cp.async.  Row words of the first passes are requested meanwhile.
-//   2. passes of 4 atoms (a quarter warp each), dealt round robin over the 16 warps from the concatenated pass list of
-//      the tile's 16 centre pencils; finished forces go to the CTA's stash.
+//   2. passes of 4 atoms (a quarter warp each): four consecutive rows of the tile, dealt round robin over the 16 warps;
+//      the three force sums of an atom go through one split butterfly into the CTA's stash.
 //   3. epilogue with one thread per atom: store f, or finalIntegrate(n) + initialIntegrate(n+1) (ref/integrate.cpp:46-68).
 template <class T, int EV, int UNIFORM, int INTEG>
 __global__ void __launch_bounds__(TILE_THREADS, 2)
@@ -401,7 +401,7 @@ force_lj_dealt_kernel(const Vec4<T>* __restrict__ x, Vec4<T>* __restrict__ f, Ti
   }
 
   // centre pencils, held by EVERY warp in the registers of lanes 0..15: {first tile-local index, atoms, first row,
-  // CSR slot of tile-local index 0} and the exclusive prefix of the pencils' pass counts
+  // CSR slot of tile-local index 0}
   int4 pcl = make_int4(0, 0, 0, 0);
   if (lane < TILE_NCENTER) {
     const int4 ce = __ldg(tc + lane);
